@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the SPH hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, via the C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on host cores
+
+A "step" is one Update(1/60) of the whole scene (demo4.cpp:286-451).  Workload at N=1 is BASELINE.json
+configs[2]: the 1M-particle dam-break block (see WORKLOADS below and DESIGN.md); with N>1 every rank owns
+a y-strip of a scene N times larger (weak scaling).  One JSON line is printed by rank 0.
+
+Timing: CUDA events on the simulation's own stream (sph_mark / sph_elapsed_ms), W >= 3 warm-up steps, a
+barrier + device synchronize on both sides, max over ranks.  The state (~90 B/particle + 8 B/cell, >130 MB at
+1M particles... plus the cell arrays) is streamed once per phase, and the L2 is additionally flushed between
+the warm-up and the timed region; `config.l2` says so.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT = float(np.float32(1.0) / np.float32(60.0))
+METRIC = "particle_steps_per_s"
+UNIT = "particle-steps/s"
+
+# BASELINE.json configs[2] / SURVEY.md 8(d) c3.  nx*nx particles per GPU.
+WORKLOADS = {
+    "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=True, relaxation=0.5),
+}
+BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
+BYTES_PER_CELL_STEP = 16
+# algorithmic HBM bytes per particle of each phase (DESIGN.md "kernels")
+PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "reorder": 44, "density": 16, "delta": 24, "collide_velocity": 32}
+KERNELS_PER_STEP = 13  # begin, integrate, viscosity, predict_key, 3 x scan, scatter_ids, reorder, density, delta, collide_velocity, commit
+
+
+def scene_gravity(nx, spacing, scaled):
+    """Dam break under the reference's gravity (0,-10) scaled so that the hydrostatic head matches the
+    reference scene (5.34 units of fluid, sph.h:310): fixed dt = 1/60 and h = 0.3 are only stable when
+    |v| dt stays below h ("scene scaling")."""
+    height = nx * spacing
+    return (0.0, -10.0 * min(1.0, 5.34375 / height)) if scaled else (0.0, -10.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from nbodysimulation_experiment_b200 import SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, pinned_empty, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = WORKLOADS[args.workload]
+    nx = args.nx or wl["nx"]
+    spacing = wl["spacing"]
+    fp_mode = SPH_FP_FAST if args.fp == "fast" else SPH_FP_EXACT
+    gravity = scene_gravity(nx, spacing, wl["gravity_scale"])
+
+    def make(flags=0):
+        sim = scenes.block_scene(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=wl["relaxation"], device=local_rank)
+        return scenes.fill_block(sim)
+
+    if world > 1:
+        raise SystemExit("multi-GPU strips are not wired in this build")
+
+    sim = make()
+    n = sim.GetParticleCount()
+    gx, gy = sim.grid_dims()
+    cells = gx * gy
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        sim.Sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        sim.Update(DT)
+    flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sim.mark(0)
+    for _ in range(args.steps):
+        sim.Update(DT)
+    sim.mark(1)
+    ms = sim.elapsed_ms(0, 1)
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = sim.GetStats()
+    value = n * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: Update + Render readback (positions + colours, creation order) into pinned host memory,
+    # the per-frame traffic of the reference's app loop (app.cpp:231-233,286-289) -------------------
+    pos_host, own_p = pinned_empty((n, 2), np.float32)
+    col_host, own_c = pinned_empty((n, 4), np.float32)
+    e2e_steps = max(3, min(args.steps, 64))
+    params_blob = np.zeros(16, np.float32)  # per-step host inputs: dt, gravity, external force (bytes counted below)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.SetGravity(gravity)
+        sim.Update(DT)
+        sim.Render(pos_host, col_host)  # D2H inside, synchronises
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n * world * e2e_steps / e2e_s
+    assert np.isfinite(pos_host).all()
+    own_p.free()
+    own_c.free()
+    sim.close()
+
+    # ---- per-phase device times (separate pass: the event brackets serialise host and device) --------
+    roofline = None
+    phases = None
+    if rank == 0:
+        psim = make(flags=SPH_FLAG_PHASE_TIMING)
+        for _ in range(3):
+            psim.Update(DT)
+        psim.ResetStats()
+        for _ in range(max(3, min(args.steps, 20))):
+            psim.Update(DT)
+        phases, _ = psim.phase_ms()
+        psim.close()
+        peak, peak_src = measured_peak_gbs()
+        dom = max((k for k in phases if k != "exchange"), key=lambda k: phases[k])
+        dom_bytes = PHASE_BYTES[dom] * n
+        achieved = dom_bytes / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
+        step_bytes = BYTES_PER_PARTICLE_STEP * n + BYTES_PER_CELL_STEP * cells
+        roofline = {
+            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+            "kernel_ms": phases[dom],
+            "step_model": {"bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                           "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "note": "the gather kernels are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/",
+        }
+
+    cpu = cpu_baseline(nx, spacing, gravity, wl["relaxation"]) if (rank == 0 and world == 1 and not args.no_cpu) else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {nx}x{nx} = {n} particles/GPU, spacing {spacing}, h = cell = 0.3, dt = 1/60, "
+                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, relaxation {wl['relaxation']}",
+                       "particles": n * world, "cells": cells, "candidates_per_particle": stats.pair_candidates / max(n, 1),
+                       "l2": "state streamed once per phase (>130 MB/step) and a 256 MiB L2 flush before the timed region",
+                       "parallelism": f"ystrip{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(n * 24),
+                    "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4) to pinned host memory"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+            "phases_ms": phases,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def oracle_scene(nx, spacing, gravity, threads, mode):
+    from oracle_lib import CpuSim
+
+    width = 4.0 * nx * spacing
+    height = width * 9.0 / 16.0
+    cell = float(np.float32(6.0) * np.float32(0.05))
+    sim = CpuSim("oracle", width=width, height=height, cell=cell, mode=mode, threads=threads)
+    p = sim.params()
+    p[2] = spacing
+    sim.put_params(p)
+    sim.set_gravity(float(gravity[0]), float(gravity[1]))
+    for a, b, d in ((0.0, 1.0, -height / 2), (0.0, -1.0, -height / 2), (1.0, 0.0, -width / 2), (-1.0, 0.0, -width / 2)):
+        sim.add_plane(a, b, float(np.float32(d)))
+    sim.add_volume(-width / 2 + nx * spacing / 2 + 0.05, -height / 2 + nx * spacing / 2 + 0.05, 0.0, 0.0, nx, nx, spacing)
+    return sim
+
+
+def cpu_baseline(nx, spacing, gravity, relaxation, budget_s=20.0):
+    """The oracle in the reference's own multithreaded mode (in-place pair updates, thread-pool split of
+    threading.h:111-129) on all host cores, on a bounded sample of the same scene."""
+    from oracle_lib import MODE_GS_INDEX, build_oracle
+
+    build_oracle()
+    cores = os.cpu_count() or 1
+    sample_nx = min(nx, 256)  # 65 536 particles of the same lattice, parameters and gravity
+    sim = oracle_scene(sample_nx, spacing, gravity, cores, MODE_GS_INDEX)
+    n = sim.n
+    sim.advance(DT, 1)
+    t = sim.advance_timed(DT, 1)
+    steps = int(max(2, min(64, budget_s / max(t, 1e-3))))
+    secs = sim.advance_timed(DT, steps)
+    sim.close()
+    return {"value": n * steps / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of a {sample_nx}x{sample_nx} = {n} particle block of the same scene (oracle gs_index mt mode)"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm for the same config on the box's host cores.
+    libsphref.so (the reference's own code) is hard-capped at 10 000 particles and a 10 x 5.625 domain
+    (sph.h:18-72), so the 1M scene runs through the oracle port in the reference's multithreaded mode."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle_lib import MODE_GS_INDEX, REF_SO, CpuSim, build_oracle
+
+    build_oracle()
+    wl = WORKLOADS[args.workload]
+    nx = args.nx or wl["nx"]
+    spacing = wl["spacing"]
+    gravity = scene_gravity(nx, spacing, wl["gravity_scale"])
+    cores = os.cpu_count() or 1
+    # bounded sample: shrink the block until K + W steps fit in ~3 minutes
+    sample_nx = min(nx, 256)
+    while True:
+        sim = oracle_scene(sample_nx, spacing, gravity, cores, MODE_GS_INDEX)
+        sim.advance(DT, 1)
+        t = sim.advance_timed(DT, 1)
+        if t * (args.steps + args.warmup) < 170.0 or sample_nx <= 32:
+            break
+        sim.close()
+        sample_nx //= 2
+    n = sim.n
+    sim.advance(DT, max(args.warmup - 2, 0))
+    secs = sim.advance_timed(DT, args.steps)
+    sim.close()
+    value = n * args.steps / secs
+    extra = None
+    if os.path.exists(REF_SO):  # the reference's own binary on ITS default scene (configs[0]), for orientation
+        ref = CpuSim("ref", threads=cores)
+        ref.load_scenario(0, 1)
+        ref.advance(DT, 8)
+        s = ref.advance_timed(DT, 64)
+        extra = {"value": ref.n * 64 / s, "unit": UNIT, "what": "libsphref.so (unmodified demo4.cpp) scenario 0, 5300 particles, 64 steps, MT"}
+        ref.close()
+    sample = f"{args.steps} steps of a {sample_nx}x{sample_nx} = {n} particle block of the same scene"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: oracle port of demo4 (gs_index, mt) on host cores; {sample}", "particles": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_binary_scene0": extra,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dambreak_1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=0, help="override the block edge (particles = nx*nx per GPU)")
+    ap.add_argument("--fp", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

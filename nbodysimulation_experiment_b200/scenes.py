@@ -1,0 +1,71 @@
+"""Synthetic large scenes of BASELINE.json `configs`: a square block of particles
+resting in the lower-left corner of a 16:9 domain four block-widths wide, like the reference's
+dam (sph.h:307-310, 316-329), with the reference's constants h = cell = 0.3, dt = 1/60.
+
+The particles come from `sph_add_volume_hashed` (AddVolume's lattice, demo4.cpp:169-181, with a
+counter-hash jitter generated on the device), so nothing is built on the host.
+"""
+import numpy as np
+
+from . import _lib
+from .simulation import ParticleSimulation
+
+KERNEL_HEIGHT = float(np.float32(6.0) * np.float32(0.05))  # sph.h:35-36
+
+
+def _domain(nx, spacing):
+    width = 4.0 * nx * spacing
+    return width, width * 9.0 / 16.0
+
+
+def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mode=_lib.SPH_FP_EXACT, flags=0,
+                relaxation=1.0, device=0, rank=0, world_size=1, capacity=None, near_stiffness=None, **params):
+    """c3 / c4: nx x ny block (default square), 4 boundary planes, dam-break under gravity."""
+    ny = nx if ny is None else ny
+    width, height = _domain(nx, spacing)
+    n = nx * ny
+    if capacity is None:
+        capacity = n + 1024 if world_size == 1 else int(n / world_size * 1.6) + 65536
+    sim = ParticleSimulation(domain_width=width, domain_height=height, cell_size=KERNEL_HEIGHT, max_particles=capacity,
+                             device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size)
+    p = sim.GetParams()
+    p.particle_spacing = spacing
+    if near_stiffness is not None:
+        p.near_stiffness = near_stiffness
+    for k, v in params.items():
+        setattr(p, k, v)
+    sim.SetParams(p)
+    sim.SetGravity(gravity)
+    hw, hh = width * 0.5, height * 0.5
+    sim.AddPlane((0.0, 1.0), -hh)   # floor: n.p = d with p = (0,-hh)
+    sim.AddPlane((0.0, -1.0), -hh)  # ceiling
+    sim.AddPlane((1.0, 0.0), -hw)   # left wall
+    sim.AddPlane((-1.0, 0.0), -hw)  # right wall
+    cx = -hw + nx * spacing * 0.5 + 0.05
+    cy = -hh + ny * spacing * 0.5 + 0.05
+    sim.scene = {"nx": nx, "ny": ny, "spacing": spacing, "center": (cx, cy), "seed": seed, "width": width, "height": height}
+    return sim
+
+
+def fill_block(sim):
+    sc = sim.scene
+    sim.AddVolumeHashed(sc["center"], (0.0, 0.0), sc["nx"], sc["ny"], sc["spacing"], sc["seed"])
+    return sim
+
+
+def bodies_scene(nx, spacing=0.1, seed=1337, **kw):
+    """c5: block + rigid circles and tilted boxes a la "Fun" (sph.h:420-436), 10x viscosity."""
+    sim = block_scene(nx, spacing=spacing, seed=seed, linear_viscosity=5.0, quadratic_viscosity=3.0, **kw)
+    w, h = sim.scene["width"], sim.scene["height"]
+    s = nx * spacing  # block edge
+    hw, hh = w * 0.5, h * 0.5
+    sim.AddCircle((-hw + 1.6 * s, -hh + 0.20 * s), 0.18 * s)
+    sim.AddCircle((-hw + 2.4 * s, -hh + 0.10 * s), 0.10 * s)
+    sim.AddCircle((-hw + 3.2 * s, -hh + 0.25 * s), 0.20 * s)
+    for (cx, cy, ang, ex, ey) in ((-hw + 2.0 * s, -hh + 0.6 * s, -2.5, 0.45 * s, 0.02 * s), (-hw + 3.0 * s, -hh + 0.45 * s, 2.5, 0.45 * s, 0.02 * s)):
+        a = np.deg2rad(ang)
+        c, sn = np.cos(a), np.sin(a)
+        local = np.array([(ex, ey), (-ex, ey), (-ex, -ey), (ex, -ey)])
+        verts = np.stack([c * local[:, 0] - sn * local[:, 1] + cx, sn * local[:, 0] + c * local[:, 1] + cy], 1)
+        sim.AddPolygon(verts.astype(np.float32))
+    return sim

@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's plugin interface for the SPH hot path.
+
+`ParticleSimulation` keeps the method names, argument meaning and call order of
+`class BaseSimulation` (/root/reference/NBodySimulation/base.h:8-39) as implemented by
+`Demo4::ParticleSimulation` (demo4.h:137-226), so tests read like calls into the reference.  Every
+method forwards to one entry point of the C ABI (include/sphb200.h); no arithmetic of the hot path
+happens in Python.  (The C++ adapter a maintainer would add to the reference itself is in
+INTEGRATION.md.)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SphConfig, SphParams, SphStats
+
+PARAM_FIELDS = [n for n, _ in SphParams._fields_]
+
+
+class SphError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"sphb200 error {code}: {text}")
+        self.code = code
+
+
+class ParticleSimulation:
+    """One simulation in HBM.  Defaults are the reference's compile-time world (sph.h:18-72)."""
+
+    def __init__(self, domain_width=None, domain_height=None, cell_size=None, max_particles=None, device=0,
+                 fp_mode=_lib.SPH_FP_EXACT, flags=0, relaxation=1.0, rank=0, world_size=1, halo_capacity=0):
+        self._lib = _lib.load()
+        cfg = SphConfig()
+        self._check(self._lib.sph_config_default(C.byref(cfg)), None)
+        if domain_width is not None:
+            cfg.domain_width = domain_width
+        if domain_height is not None:
+            cfg.domain_height = domain_height
+        if cell_size is not None:
+            cfg.cell_size = cell_size
+        if max_particles is not None:
+            cfg.max_particles = int(max_particles)
+        cfg.device = device
+        cfg.fp_mode = fp_mode
+        cfg.flags = flags
+        cfg.relaxation = relaxation
+        cfg.rank = rank
+        cfg.world_size = world_size
+        cfg.halo_capacity = halo_capacity
+        self.config = cfg
+        self._h = _lib.c_vp()
+        self._check(self._lib.sph_create(C.byref(cfg), C.byref(self._h)), None)
+        self._multithreading = True
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _check(self, rc, handle="self"):
+        if rc == _lib.SPH_OK:
+            return
+        buf = C.create_string_buffer(512)
+        self._lib.sph_last_error(self._h if handle == "self" else None, buf, 512)
+        raise SphError(rc, buf.value.decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- BaseSimulation surface (base.h:10-38), same names ----------------------------------
+    def ResetStats(self):
+        self._check(self._lib.sph_reset_stats(self._h))
+
+    def ClearBodies(self):
+        self._check(self._lib.sph_clear_bodies(self._h))
+
+    def ClearParticles(self):
+        self._check(self._lib.sph_clear_particles(self._h))
+
+    def ClearEmitters(self):
+        self._check(self._lib.sph_clear_emitters(self._h))
+
+    def AddPlane(self, normal, distance):
+        self._check(self._lib.sph_add_plane(self._h, normal[0], normal[1], distance))
+
+    def AddCircle(self, pos, radius):
+        self._check(self._lib.sph_add_circle(self._h, pos[0], pos[1], radius))
+
+    def AddLineSegment(self, a, b):
+        self._check(self._lib.sph_add_segment(self._h, a[0], a[1], b[0], b[1]))
+
+    def AddPolygon(self, verts):
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1)
+        self._check(self._lib.sph_add_polygon(self._h, len(v) // 2, v.ctypes.data))
+
+    def AddParticle(self, position, force=(0.0, 0.0)):
+        return self.AddParticles(np.array([position], np.float32), np.array([force], np.float32))
+
+    def AddParticles(self, positions, forces=None):
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+        f = None if forces is None else np.ascontiguousarray(forces, np.float32).reshape(-1, 2)
+        first = C.c_uint64()
+        self._check(self._lib.sph_add_particles(self._h, len(p), p.ctypes.data, None if f is None else f.ctypes.data, C.byref(first)))
+        return first.value
+
+    def AddVolume(self, center, force, countX, countY, spacing):
+        self._check(self._lib.sph_add_volume(self._h, center[0], center[1], force[0], force[1], countX, countY, spacing))
+
+    def AddVolumeHashed(self, center, force, countX, countY, spacing, seed=1337):
+        self._check(self._lib.sph_add_volume_hashed(self._h, center[0], center[1], force[0], force[1], countX, countY, spacing, seed))
+
+    def AddEmitter(self, position, direction, radius, speed, rate, duration):
+        self._check(self._lib.sph_add_emitter(self._h, position[0], position[1], direction[0], direction[1], radius, speed, rate, duration))
+
+    def Update(self, deltaTime):
+        self._check(self._lib.sph_step(self._h, deltaTime))
+
+    def Render(self, positions=None, colors=None):
+        """The particle section of Render() (demo4.cpp:520-531): positions + colours, creation order."""
+        n = self.GetParticleCount()
+        if positions is None:
+            positions = np.empty((n, 2), np.float32)
+        if colors is None:
+            colors = np.empty((n, 4), np.float32)
+        self._check(self._lib.sph_render_particles(self._h, positions.ctypes.data, positions.strides[0], colors.ctypes.data, colors.strides[0]))
+        self.Sync()
+        return positions, colors
+
+    def AddExternalForces(self, force):
+        self._check(self._lib.sph_add_external_force(self._h, force[0], force[1]))
+
+    def ClearExternalForce(self):
+        self._check(self._lib.sph_clear_external_force(self._h))
+
+    def GetParticleCount(self):
+        out = C.c_uint64()
+        self._check(self._lib.sph_particle_count(self._h, C.byref(out)))
+        return out.value
+
+    def SetGravity(self, gravity):
+        self._check(self._lib.sph_set_gravity(self._h, gravity[0], gravity[1]))
+
+    def GetParams(self):
+        p = SphParams()
+        self._check(self._lib.sph_get_params(self._h, C.byref(p)))
+        return p
+
+    def SetParams(self, params):
+        if not isinstance(params, SphParams):
+            arr = np.asarray(params, np.float32)
+            p = SphParams(*[float(x) for x in arr])
+        else:
+            p = params
+        self._check(self._lib.sph_set_params(self._h, C.byref(p)))
+
+    def GetStats(self):
+        st = SphStats()
+        self._check(self._lib.sph_get_stats(self._h, C.byref(st)))
+        return st
+
+    def SetMultiThreading(self, value):  # the GPU path has one mode; kept for interface parity
+        self._multithreading = bool(value)
+
+    def IsMultiThreadingSupported(self):
+        return True
+
+    def IsMultiThreading(self):
+        return self._multithreading
+
+    def GetWorkerThreadCount(self):
+        return 148  # one worker per SM of the B200 the kernels are sized for
+
+    # -- beyond base.h: scenes, passes, readback ---------------------------------------------
+    def LoadScenario(self, index, seed=-1):
+        """DemoApplication::LoadScenario (app.cpp:477-534) for SPHScenarios[index] (sph.h:315-437)."""
+        self._check(self._lib.sph_load_scenario(self._h, index, seed))
+
+    def SetRelaxation(self, omega):
+        self._check(self._lib.sph_set_relaxation(self._h, omega))
+
+    def RunPass(self, which, dt=1.0 / 60.0):
+        self._check(self._lib.sph_run_pass(self._h, which, dt))
+
+    def Sync(self):
+        self._check(self._lib.sph_sync(self._h))
+
+    def grid_dims(self):
+        gx, gy = C.c_int32(), C.c_int32()
+        self._check(self._lib.sph_grid_dims(self._h, C.byref(gx), C.byref(gy)))
+        return gx.value, gy.value
+
+    def params_array(self):
+        p = self.GetParams()
+        return np.array([getattr(p, n) for n in PARAM_FIELDS], np.float32)
+
+    def particles(self):
+        """(n, 12) float32 in ParticleData order (demo4.h:81-99), creation order."""
+        n = self.GetParticleCount()
+        out = np.zeros((n, 12), np.float32)
+        if n:
+            self._check(self._lib.sph_read_particles(self._h, out.ctypes.data, 48))
+        return out
+
+    def put_particles(self, arr):
+        arr = np.ascontiguousarray(arr, np.float32)
+        assert arr.shape == (self.GetParticleCount(), 12)
+        self._check(self._lib.sph_write_particles(self._h, arr.ctypes.data, 48))
+
+    def cell_counts(self):
+        gx, gy = self.grid_dims()
+        out = np.zeros(gx * gy, np.uint32)
+        self._check(self._lib.sph_read_cell_counts(self._h, out.ctypes.data))
+        return out
+
+    def cell_start(self):
+        gx, gy = self.grid_dims()
+        out = np.zeros(gx * gy + 1, np.uint32)
+        self._check(self._lib.sph_read_cell_start(self._h, out.ctypes.data))
+        return out
+
+    def sorted_ids(self):
+        out = np.zeros(self.GetParticleCount(), np.uint32)
+        self._check(self._lib.sph_read_sorted_ids(self._h, out.ctypes.data))
+        return out
+
+    def cell_of_particle(self):
+        out = np.zeros((self.GetParticleCount(), 2), np.int32)
+        self._check(self._lib.sph_read_cell_of_particle(self._h, out.ctypes.data))
+        return out
+
+    def phase_ms(self):
+        arr = (C.c_float * _lib.SPH_NUM_PHASES)()
+        steps = C.c_uint64()
+        self._check(self._lib.sph_get_phase_ms(self._h, C.byref(arr), C.byref(steps)))
+        return dict(zip(_lib.PHASE_NAMES, [float(x) for x in arr])), steps.value
+
+    def mark(self, slot):
+        self._check(self._lib.sph_mark(self._h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self._lib.sph_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def stream_ptr(self):
+        out = _lib.c_vp()
+        self._check(self._lib.sph_get_stream(self._h, C.byref(out)))
+        return out.value
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy view of page-locked host memory from sph_host_alloc (freed with the returned owner)."""
+    lib = _lib.load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = _lib.c_vp()
+    if lib.sph_host_alloc(C.byref(ptr), max(nbytes, 1)) != 0:
+        raise SphError(-3, "sph_host_alloc failed")
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def free(self):
+            if self.p:
+                lib.sph_host_free(self.p)
+                self.p = None
+
+    return arr, _Owner(ptr)
