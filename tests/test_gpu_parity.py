@@ -127,11 +127,11 @@ def test_grid_and_density_from_reference_state(pkg, path):
     gpu.SetParams(p)
     gpu.AddParticles(last[:, 0:2])
     gpu.put_particles(last)  # re-files the grid
-    assert np.array_equal(gpu.cell_of_particle(), g["cell_of_particle"])
-    assert np.array_equal(gpu.cell_counts(), g["cell_counts"])
+    assert np.array_equal(gpu.cell_of_particle(), g["refiled_cell_of_particle"])
+    assert np.array_equal(gpu.cell_counts(), g["refiled_cell_counts"])
     ids, start = gpu.sorted_ids(), gpu.cell_start()
     gx, gy = gpu.grid_dims()
-    cells = g["cell_of_particle"]
+    cells = g["refiled_cell_of_particle"]
     sums = np.zeros(n, np.uint64)
     xors = np.zeros(n, np.uint32)
     lens = np.zeros(n, np.uint32)
@@ -140,8 +140,8 @@ def test_grid_and_density_from_reference_state(pkg, path):
         lens[i] = len(nb)
         sums[i] = nb.astype(np.uint64).sum()
         xors[i] = np.bitwise_xor.reduce(nb * np.uint32(2654435761)) if len(nb) else 0
-    assert np.array_equal(lens, g["neighbor_counts"])
-    assert np.array_equal(sums, g["cand_sum"]) and np.array_equal(xors, g["cand_xor"])
+    assert np.array_equal(lens, g["refiled_neighbor_counts"])
+    assert np.array_equal(sums, g["refiled_cand_sum"]) and np.array_equal(xors, g["refiled_cand_xor"])
     gpu.RunPass(pkg._lib.PASS_DENSITY, DT)
     d = gpu.particles()[:, 8:12]
     np.testing.assert_allclose(d, g["density_from_last"], rtol=2e-5, atol=2e-5)

@@ -54,4 +54,9 @@ def test_oracle_matches_reference_dump(path):
     sim.pass_neighbor_search()
     sim.pass_density()
     assert np.array_equal(sim.particles()[:, 8:12], g["density_from_last"])
+    assert np.array_equal(sim.cell_of_particle(), g["refiled_cell_of_particle"])
+    assert np.array_equal(sim.cell_counts(), g["refiled_cell_counts"])
+    assert np.array_equal(sim.neighbor_counts(), g["refiled_neighbor_counts"])
+    sums, xors = candidate_checksums(sim)
+    assert np.array_equal(sums, g["refiled_cand_sum"]) and np.array_equal(xors, g["refiled_cand_xor"])
     sim.close()

@@ -68,6 +68,12 @@ def main():
         sim.neighbor_search(DT)
         sim.density_pressure(DT)
         data["density_from_last"] = sim.particles()[:, 8:12].copy()
+        # the integer side of that re-filed grid (the step's own grid above was filed from the
+        # PREDICTED positions, demo4.cpp:342-356, so it is stale with respect to the final state)
+        data["refiled_cell_of_particle"] = sim.cell_of_particle()
+        data["refiled_cell_counts"] = sim.cell_counts()
+        data["refiled_neighbor_counts"] = sim.neighbor_counts()
+        data["refiled_cand_sum"], data["refiled_cand_xor"] = candidate_checksums(sim)
         path = os.path.join(OUT, f"scene{scene}.npz")
         np.savez_compressed(path, **data)
         print(f"scene {scene}: n={sim.n} steps={steps} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
