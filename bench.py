@@ -34,13 +34,14 @@ UNIT = "particle-steps/s"
 
 # BASELINE.json configs[2] / SURVEY.md 8(d) c3.  nx*nx particles per GPU.
 WORKLOADS = {
-    "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=True, relaxation=0.5),
+    "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=False, relaxation=1.0),
 }
 BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
 # algorithmic HBM bytes per particle of each phase (DESIGN.md "kernels")
 PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "reorder": 44, "density": 16, "delta": 24, "collide_velocity": 32}
-KERNELS_PER_STEP = 13  # begin, integrate, viscosity, predict_key, 3 x scan, scatter_ids, reorder, density, delta, collide_velocity, commit
+# begin, integrate, 9 x viscosity sweep, predict_key, 3 x scan, colour lists, scatter_ids, reorder, density, 9 x delta sweep, collide_velocity, commit
+KERNELS_PER_STEP = {"gs": 30, "gather": 13}
 
 
 def scene_gravity(nx, spacing, scaled):
@@ -107,7 +108,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from nbodysimulation_experiment_b200 import SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, pinned_empty, scenes
+    from nbodysimulation_experiment_b200 import (SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER,
+                                                 pinned_empty, scenes)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -123,10 +125,13 @@ def run_ours(args):
     nx = args.nx or wl["nx"]
     spacing = wl["spacing"]
     fp_mode = SPH_FP_FAST if args.fp == "fast" else SPH_FP_EXACT
-    gravity = scene_gravity(nx, spacing, wl["gravity_scale"])
+    gravity = scene_gravity(nx, spacing, wl["gravity_scale"] or args.scaled_gravity)
+    solver = SPH_SOLVER_GATHER if args.solver == "gather" else SPH_SOLVER_COLORED_GS
+    relaxation = args.relaxation if args.relaxation else wl["relaxation"]
 
     def make(flags=0):
-        sim = scenes.block_scene(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=wl["relaxation"], device=local_rank)
+        sim = scenes.block_scene(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=relaxation, device=local_rank,
+                                 solver=solver, sweep_capacity=args.sweep_capacity)
         return scenes.fill_block(sim)
 
     if world > 1:
@@ -214,7 +219,7 @@ def run_ours(args):
             "note": "the gather kernels are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/",
         }
 
-    cpu = cpu_baseline(nx, spacing, gravity, wl["relaxation"]) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    cpu = cpu_baseline(nx, spacing, gravity, relaxation) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
         line = {
@@ -222,13 +227,13 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {nx}x{nx} = {n} particles/GPU, spacing {spacing}, h = cell = 0.3, dt = 1/60, "
-                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, relaxation {wl['relaxation']}",
+                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}",
                        "particles": n * world, "cells": cells, "candidates_per_particle": stats.pair_candidates / max(n, 1),
                        "l2": "state streamed once per phase (>130 MB/step) and a 256 MiB L2 flush before the timed region",
                        "parallelism": f"ystrip{world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(n * 24),
                     "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4) to pinned host memory"},
-            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "gpu_launches": KERNELS_PER_STEP[args.solver] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
             "phases_ms": phases,
@@ -289,7 +294,7 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     nx = args.nx or wl["nx"]
     spacing = wl["spacing"]
-    gravity = scene_gravity(nx, spacing, wl["gravity_scale"])
+    gravity = scene_gravity(nx, spacing, wl["gravity_scale"] or args.scaled_gravity)
     cores = os.cpu_count() or 1
     # bounded sample: shrink the block until K + W steps fit in ~3 minutes
     sample_nx = min(nx, 256)
@@ -337,6 +342,10 @@ def main():
     ap.add_argument("--nx", type=int, default=0, help="override the block edge (particles = nx*nx per GPU)")
     ap.add_argument("--fp", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solver", default="gs", choices=["gs", "gather"], help="coloured Gauss-Seidel sweeps (default) or Jacobi gather")
+    ap.add_argument("--relaxation", type=float, default=0.0, help="gather only: omega")
+    ap.add_argument("--sweep-capacity", type=int, default=0)
+    ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

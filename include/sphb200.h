@@ -46,6 +46,16 @@ typedef enum SphStatus {
  *          and the velocity update stay exact in both modes. */
 enum { SPH_FP_EXACT = 0, SPH_FP_FAST = 1 };
 
+/* solver: how the two in-place pair sweeps of the reference (viscosity, demo4.cpp:223-237, and
+ * pressure displacement, demo4.cpp:239-255) are parallelised.
+ *   COLORED_GS: the reference's own in-place half-weight pair updates, swept race-free over nine
+ *               cell colours (cx mod 3, cy mod 3), ascending id inside a cell.  Keeps the
+ *               Gauss-Seidel self-damping the reference relies on; the default.
+ *   GATHER    : every pair term evaluated from the pass's input state and summed per particle
+ *               (Jacobi); cheaper to exchange across GPUs but unstable on stiff scenes unless
+ *               under-relaxed (SphConfig.relaxation). */
+enum { SPH_SOLVER_COLORED_GS = 0, SPH_SOLVER_GATHER = 1 };
+
 enum {
 	SPH_FLAG_PHASE_TIMING = 1u << 0 /* bracket every phase with CUDA events and fill SphStats.time_* (sph.h:131-141) */
 };
@@ -60,7 +70,9 @@ typedef struct SphConfig {
 	int32_t device;          /* CUDA device ordinal */
 	int32_t fp_mode;         /* SPH_FP_EXACT | SPH_FP_FAST */
 	uint32_t flags;          /* SPH_FLAG_* */
-	float relaxation;        /* omega of the displacement gather, x += omega*dx (1 = plain Jacobi) */
+	float relaxation;        /* GATHER only: omega of the displacement pass, x += omega*dx (1 = plain Jacobi) */
+	int32_t solver;          /* SPH_SOLVER_COLORED_GS | SPH_SOLVER_GATHER */
+	uint32_t sweep_capacity; /* COLORED_GS: candidates of one 3x3 block staged in shared memory (0 = 512) */
 	/* y-strip decomposition; world_size = 1 for a single GPU */
 	int32_t rank;
 	int32_t world_size;

@@ -5,11 +5,12 @@ include/sphb200.h, built into libsphb200.so) and the host-side mirror of the ref
 `BaseSimulation` interface (`ParticleSimulation`).  There is no CPU or PyTorch fallback.
 """
 from . import _lib
-from ._lib import SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SphConfig, SphParams, SphStats
+from ._lib import (SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER, SphConfig,
+                   SphParams, SphStats)
 from .scenes import block_scene, bodies_scene
 from .simulation import ParticleSimulation, SphError, pinned_empty
 
 __all__ = [
     "ParticleSimulation", "SphError", "SphConfig", "SphParams", "SphStats", "pinned_empty",
-    "SPH_FP_EXACT", "SPH_FP_FAST", "SPH_FLAG_PHASE_TIMING", "block_scene", "bodies_scene",
+    "SPH_FP_EXACT", "SPH_FP_FAST", "SPH_FLAG_PHASE_TIMING", "SPH_SOLVER_COLORED_GS", "SPH_SOLVER_GATHER", "block_scene", "bodies_scene",
 ]

@@ -17,6 +17,8 @@ SPH_OK = 0
 SPH_FP_EXACT = 0
 SPH_FP_FAST = 1
 SPH_FLAG_PHASE_TIMING = 1
+SPH_SOLVER_COLORED_GS = 0
+SPH_SOLVER_GATHER = 1
 SPH_NUM_PHASES = 9
 PHASE_NAMES = ("integrate", "viscosity", "predict_key", "scan", "reorder", "density", "delta", "collide_velocity", "exchange")
 
@@ -34,6 +36,8 @@ class SphConfig(C.Structure):
         ("fp_mode", c_i32),
         ("flags", C.c_uint32),
         ("relaxation", c_f),
+        ("solver", c_i32),
+        ("sweep_capacity", C.c_uint32),
         ("rank", c_i32),
         ("world_size", c_i32),
         ("halo_capacity", c_u64),

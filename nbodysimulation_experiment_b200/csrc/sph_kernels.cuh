@@ -336,6 +336,208 @@ __global__ void __launch_bounds__(SPH_THREADS) delta_kernel(GridDesc g, PairPara
 	}
 }
 
+// ---- 9-colour cell Gauss-Seidel: the reference's in-place pair sweeps, race-free ------------------
+// demo4.cpp:223-255 updates BOTH particles of every pair in place, in particle-index order.  That
+// order is what keeps the double-density relaxation stable (each pair sees the displacements of
+// the pairs before it); a plain gather of all pair terms from the old state overshoots and blows
+// up on stiff scenes ("why not Jacobi").  Cells whose (cx mod 3, cy mod 3) agree have
+// disjoint 3x3 footprints, so the nine colours are swept one launch after another; inside a
+// launch ONE WARP owns one cell, walks its particles by ascending id, and spreads each particle's
+// candidate loop over its 32 lanes (candidate k belongs to lane k mod 32 for the whole sweep, so a
+// staged candidate is only ever written by one lane).  The partner is updated at once, the
+// particle's own change is summed per lane, combined by a xor butterfly and applied at the end
+// of its loop (demo4.cpp:253).  The 3x3 block is staged in shared memory; blocks larger than the
+// staging capacity take the same algorithm through L2 (__ldcg/__stcg).
+#define SPH_SWEEP_WARPS 4
+
+// occupied cells of each colour, rebuilt with the grid (order inside a list is irrelevant: the
+// footprints of one colour are disjoint)
+__global__ void __launch_bounds__(SPH_THREADS) color_lists_kernel(GridDesc g, const uint32_t *__restrict__ cellStart, uint32_t *__restrict__ colorCount,
+                                                                 uint32_t *__restrict__ colorList, uint32_t listStride) {
+	const uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+	const uint32_t c = base + lane_id();
+	int color = -1;
+	if (c < g.nCells && cellStart[c + 1] > cellStart[c]) {
+		const uint32_t yl = c / (uint32_t)g.gx, cx = c - yl * (uint32_t)g.gx;
+		color = (int)(((yl + (uint32_t)g.rowLo) % 3u) * 3u + cx % 3u);
+	}
+#pragma unroll
+	for (int k = 0; k < 9; ++k) {
+		const uint32_t mask = __ballot_sync(0xffffffffu, color == k);
+		if (!mask) continue;
+		const int leader = __ffs(mask) - 1;
+		uint32_t at = 0;
+		if ((int)lane_id() == leader) at = atomicAdd(&colorCount[k], (uint32_t)__popc(mask));
+		at = __shfl_sync(0xffffffffu, at, leader);
+		if (color == k) colorList[(uint32_t)k * listStride + at + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u))] = c;
+	}
+}
+
+enum { SWEEP_DELTA = 0, SWEEP_VISCOSITY = 1 };
+
+template <class M>
+__device__ __forceinline__ float2 sweep_delta_term(const PairParams &k, float2 xi, float2 ppi, float2 xj, bool &hit) {
+	// SPHComputeDelta, sph.h:483-495, then * 0.5f (demo4.cpp:250-251)
+	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+	float r2 = M::dot2(rx, rx, ry, ry);
+	hit = r2 < k.h2;
+	if (!hit) return make_float2(0.0f, 0.0f);
+	float r, inv;
+	M::len_inv(r2, r, inv);
+	float t = M::sub(1.0f, M::mul(r, k.invH));
+	float d = M::mul(k.dt2, M::add(M::mul(ppi.x, t), M::mul(ppi.y, M::mul(t, t))));
+	return make_float2(M::mul(M::mul(d, M::mul(rx, inv)), 0.5f), M::mul(M::mul(d, M::mul(ry, inv)), 0.5f));
+}
+
+template <class M>
+__device__ __forceinline__ float2 sweep_viscosity_term(const PairParams &k, float2 xi, float2 vi, float2 xj, float2 vj, bool &hit) {
+	// SPHComputeViscosityForce, sph.h:497-512, then * 0.5f * deltaTime (demo4.cpp:233-234)
+	hit = false;
+	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+	float r2 = M::dot2(rx, rx, ry, ry);
+	if (!(r2 < k.h2)) return make_float2(0.0f, 0.0f);
+	float r, inv;
+	M::len_inv(r2, r, inv);
+	float q = M::mul(r, k.invH);
+	float nx = M::mul(rx, inv), ny = M::mul(ry, inv);
+	float u = M::dot2(M::sub(vi.x, vj.x), nx, M::sub(vi.y, vj.y), ny);
+	if (!(u > 0.0f)) return make_float2(0.0f, 0.0f);
+	hit = true;
+	float f = M::mul(M::sub(1.0f, q), M::add(M::mul(k.sigma, u), M::mul(k.beta, M::mul(u, u))));
+	return make_float2(M::mul(M::mul(M::mul(f, nx), 0.5f), k.dt), M::mul(M::mul(M::mul(f, ny), 0.5f), k.dt));
+}
+
+__device__ __forceinline__ float butterfly_sum(float v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// state = pos (SWEEP_DELTA: read+written) or vel (SWEEP_VISCOSITY: read+written, pos read-only)
+template <class M, int PASS>
+__global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
+                                                                          const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
+                                                                          float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap) {
+	extern __shared__ float2 sweepSmem[];
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+	float2 *sPos = sweepSmem + (size_t)w * cap * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+	float2 *sVel = sPos + cap; // viscosity only
+	const uint32_t nList = *colorCount;
+	const int nRows = g.rowHi - g.rowLo;
+	for (uint32_t idx = blockIdx.x * SPH_SWEEP_WARPS + w; idx < nList; idx += gridDim.x * SPH_SWEEP_WARPS) {
+		const uint32_t c = colorList[idx];
+		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
+		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
+		uint32_t lo[3], cnt[3];
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			const int y = yl - 1 + r;
+			if (y < 0 || y >= nRows) {
+				lo[r] = 0;
+				cnt[r] = 0;
+			} else {
+				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
+				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
+			}
+		}
+		const uint32_t ownLo = cellStart[c], m = cellStart[c + 1] - ownLo;
+		const uint32_t off1 = cnt[0], off2 = cnt[0] + cnt[1], T = off2 + cnt[2];
+		const uint32_t ownOff = off1 + (ownLo - lo[1]);
+		// candidate t of the block -> index in the sorted arrays
+		auto gidx = [&](uint32_t t) { return t < off1 ? lo[0] + t : (t < off2 ? lo[1] + (t - off1) : lo[2] + (t - off2)); };
+		const bool staged = T <= cap;
+		float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
+		if (staged) {
+			for (uint32_t t = lane; t < T; t += 32) {
+				const uint32_t j = gidx(t);
+				sPos[t] = pos[j];
+				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
+			}
+		}
+		__syncwarp();
+		for (uint32_t kBase = 0; kBase < m; kBase += 32) {
+			float2 myPress = make_float2(0.0f, 0.0f);
+			if (PASS == SWEEP_DELTA && kBase + lane < m) myPress = press[ownLo + kBase + lane];
+			const uint32_t kEnd = min(m - kBase, 32u);
+			for (uint32_t kk = 0; kk < kEnd; ++kk) {
+				const uint32_t si = ownOff + kBase + kk; // this particle's slot among the candidates
+				float2 xi, vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
+				if (staged) {
+					xi = sPos[si];
+					if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
+				} else {
+					xi = __ldcg(&pos[ownLo + kBase + kk]);
+					if (PASS == SWEEP_VISCOSITY) vi = __ldcg(&vel[ownLo + kBase + kk]);
+				}
+				if (PASS == SWEEP_DELTA) {
+					ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
+					ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
+				}
+				float ax = 0.0f, ay = 0.0f;
+				for (uint32_t t = lane; t < T; t += 32) {
+					bool hit;
+					if (staged) {
+						if (PASS == SWEEP_DELTA) {
+							const float2 xj = sPos[t];
+							const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+							if (hit) {
+								sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+								ax = __fsub_rn(ax, hlf.x);
+								ay = __fsub_rn(ay, hlf.y);
+							}
+						} else {
+							const float2 vj = sVel[t];
+							const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, sPos[t], vj, hit);
+							if (hit) {
+								sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+								ax = __fsub_rn(ax, hlf.x);
+								ay = __fsub_rn(ay, hlf.y);
+							}
+						}
+					} else {
+						const uint32_t j = gidx(t);
+						if (PASS == SWEEP_DELTA) {
+							const float2 xj = __ldcg(&pos[j]);
+							const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+							if (hit) {
+								__stcg(&pos[j], make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y)));
+								ax = __fsub_rn(ax, hlf.x);
+								ay = __fsub_rn(ay, hlf.y);
+							}
+						} else {
+							const float2 vj = __ldcg(&vel[j]);
+							const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, __ldcg(&pos[j]), vj, hit);
+							if (hit) {
+								__stcg(&vel[j], make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y)));
+								ax = __fsub_rn(ax, hlf.x);
+								ay = __fsub_rn(ay, hlf.y);
+							}
+						}
+					}
+				}
+				ax = butterfly_sum(ax);
+				ay = butterfly_sum(ay);
+				__syncwarp();
+				if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
+					if (staged) {
+						float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
+						*slot = make_float2(__fadd_rn(ax, slot->x), __fadd_rn(ay, slot->y));
+					} else {
+						float2 *slot = &state[ownLo + kBase + kk];
+						const float2 cur = __ldcg(slot);
+						__stcg(slot, make_float2(__fadd_rn(ax, cur.x), __fadd_rn(ay, cur.y)));
+					}
+				}
+				__syncwarp();
+			}
+		}
+		if (staged) {
+			for (uint32_t t = lane; t < T; t += 32) state[gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
+		}
+		__syncwarp();
+	}
+}
+
 // ---- phases 8+9: body collisions and velocity (demo4.cpp:412-450) ---------------------------------
 // Also closes the step: publishes n = nSorted = nOut for the next one.
 __global__ void __launch_bounds__(SPH_THREADS) collide_velocity_kernel(Counters *__restrict__ ctr, float2 *__restrict__ pos, const float2 *__restrict__ prev,

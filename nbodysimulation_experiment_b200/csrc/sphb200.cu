@@ -59,6 +59,9 @@ struct SphSim {
 	uint32_t *cellNew = nullptr, *rank = nullptr, *slotId = nullptr;
 	uint32_t *cellCount = nullptr, *cellStart = nullptr, *tileSums = nullptr;
 	uint32_t nTiles = 0;
+	// occupied cells per colour for the coloured Gauss-Seidel sweeps
+	uint32_t *colorCount = nullptr, *colorList = nullptr;
+	uint32_t listStride = 0, sweepCap = 512;
 
 	std::vector<DevBody> bodies;
 	DevBody *dBodies = nullptr;
@@ -145,6 +148,7 @@ PairParams pair_params(const SphSim *s, float dt) {
 	k.sigma = s->params.linear_viscosity;
 	k.beta = s->params.quadratic_viscosity;
 	k.dt = dt;
+	k.dt2 = dt * dt;
 	k.halfDt2 = (dt * dt) * 0.5f;
 	k.omega = s->omega;
 	return k;
@@ -254,6 +258,10 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
 	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
+	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) {
+		cudaMemsetAsync(s->colorCount, 0, 9 * sizeof(uint32_t), s->stream);
+		color_lists_kernel<<<(g.nCells + SPH_THREADS - 1) / SPH_THREADS, SPH_THREADS, 0, s->stream>>>(g, s->cellStart, s->colorCount, s->colorList, s->listStride);
+	}
 	if (timed) record_phase(s, PH_SCAN + 1);
 	scatter_ids_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->cellNew, s->rank, s->id.in(), s->cellStart, s->slotId);
 	reorder_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->cellNew, s->id.in(), s->cellStart, s->slotId, s->pos.in(), s->prev.in(), s->pos.out(),
@@ -283,9 +291,52 @@ template <class M>
 void launch_density(SphSim *s, const PairParams &k, unsigned nb) {
 	density_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->cellOf.in(), s->cellStart, s->dens.in(), s->press.in());
 }
+// nine launches, one per cell colour; in place on pos (delta) or vel (viscosity)
+template <class M, int PASS>
+void launch_sweeps(SphSim *s, const PairParams &k) {
+	const size_t smem = (size_t)SPH_SWEEP_WARPS * s->sweepCap * sizeof(float2) * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+	static bool attrSet = false;
+	if (!attrSet) {
+		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		attrSet = true;
+	}
+	// occupied cells of one colour <= min(cells of that colour, particles)
+	uint64_t cells = std::min<uint64_t>(s->listStride, std::max<uint64_t>(s->hostN, 1));
+	unsigned blocks = (unsigned)std::min<uint64_t>((cells + SPH_SWEEP_WARPS - 1) / SPH_SWEEP_WARPS, 148u * 64u);
+	for (int color = 0; color < 9; ++color)
+		color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList + (size_t)color * s->listStride,
+		                                                                             s->colorCount + color, s->pos.in(), s->vel.in(), s->press.in(), s->sweepCap);
+}
+
+int run_viscosity(SphSim *s, const PairParams &k, unsigned nb) {
+	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
+	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) {
+		if (exact) launch_sweeps<Exact, SWEEP_VISCOSITY>(s, k);
+		else launch_sweeps<Fast, SWEEP_VISCOSITY>(s, k);
+	} else {
+		if (exact) launch_viscosity<Exact>(s, k, nb);
+		else launch_viscosity<Fast>(s, k, nb);
+		s->vel.flip();
+	}
+	return SPH_OK;
+}
+
 template <class M>
 void launch_delta(SphSim *s, const PairParams &k, unsigned nb) {
 	delta_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->press.in(), s->cellOf.in(), s->cellStart, s->pos.out());
+}
+
+int run_delta(SphSim *s, const PairParams &k, unsigned nb) {
+	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
+	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) {
+		if (exact) launch_sweeps<Exact, SWEEP_DELTA>(s, k);
+		else launch_sweeps<Fast, SWEEP_DELTA>(s, k);
+	} else {
+		if (exact) launch_delta<Exact>(s, k, nb);
+		else launch_delta<Fast>(s, k, nb);
+		s->pos.flip();
+	}
+	return SPH_OK;
 }
 
 int append_particles(SphSim *s, size_t n, const float *posXY, const float *accXY, uint64_t *firstIndex) {
@@ -334,6 +385,8 @@ int sph_config_default(SphConfig *cfg) {
 	cfg->fp_mode = SPH_FP_EXACT;
 	cfg->flags = 0;
 	cfg->relaxation = 1.0f;
+	cfg->solver = SPH_SOLVER_COLORED_GS;
+	cfg->sweep_capacity = 0;
 	cfg->rank = 0;
 	cfg->world_size = 1;
 	cfg->halo_capacity = 0;
@@ -362,6 +415,15 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	s->cfg = *cfg;
 	default_params(&s->params);
 	s->omega = cfg->relaxation > 0.0f ? cfg->relaxation : 1.0f;
+	if (cfg->solver != SPH_SOLVER_COLORED_GS && cfg->solver != SPH_SOLVER_GATHER) {
+		delete s;
+		return fail(nullptr, SPH_ERR_INVALID, "unknown solver %d", cfg->solver);
+	}
+	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 512u;
+	if (s->sweepCap < 32 || s->sweepCap > 3072) {
+		delete s;
+		return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..3072", s->sweepCap);
+	}
 	GridDesc &g = s->grid;
 	g.halfW = cfg->domain_width * 0.5f;  // sph.h:21
 	g.halfH = cfg->domain_height * 0.5f; // sph.h:22
@@ -409,6 +471,10 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	CUC(cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
 	CUC(cudaMemset(s->cellStart, 0, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
+	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
+	CUC(cudaMalloc(&s->colorCount, 16 * sizeof(uint32_t)));
+	CUC(cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
+	CUC(cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->dBodies, kMaxBodies * sizeof(DevBody)));
 	for (auto &e : s->phaseEv) CUC(cudaEventCreate(&e));
 	for (auto &e : s->marks) CUC(cudaEventCreate(&e));
@@ -436,6 +502,8 @@ int sph_destroy(SphHandle s) {
 	cudaFree(s->cellCount);
 	cudaFree(s->cellStart);
 	cudaFree(s->tileSums);
+	cudaFree(s->colorCount);
+	cudaFree(s->colorList);
 	cudaFree(s->dBodies);
 	cudaFree(s->dRecords);
 	cudaFree(s->dRenderPos);
@@ -822,18 +890,14 @@ int sph_step(SphHandle s, float dt) {
 	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
 	s->accFrom = 0xFFFFFFFFu;
 	record_phase(s, PH_INTEGRATE + 1);
-	if (exact) launch_viscosity<Exact>(s, k, nb);
-	else launch_viscosity<Fast>(s, k, nb);
-	s->vel.flip();
+	run_viscosity(s, k, nb);
 	record_phase(s, PH_VISCOSITY + 1);
 	rc = launch_grid_build(s, dt, true, false, true);
 	if (rc != SPH_OK) return rc;
 	if (exact) launch_density<Exact>(s, k, nb);
 	else launch_density<Fast>(s, k, nb);
 	record_phase(s, PH_DENSITY + 1);
-	if (exact) launch_delta<Exact>(s, k, nb);
-	else launch_delta<Fast>(s, k, nb);
-	s->pos.flip();
+	run_delta(s, k, nb);
 	record_phase(s, PH_DELTA + 1);
 	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1);
 	commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
@@ -876,9 +940,7 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 			s->accFrom = 0xFFFFFFFFu;
 		} break;
 		case SPH_PASS_VISCOSITY:
-			if (exact) launch_viscosity<Exact>(s, k, nb);
-			else launch_viscosity<Fast>(s, k, nb);
-			s->vel.flip();
+			run_viscosity(s, k, nb);
 			break;
 		case SPH_PASS_PREDICT:
 			predict_only_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), dt);
@@ -895,9 +957,7 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 			else launch_density<Fast>(s, k, nb);
 			break;
 		case SPH_PASS_DELTA:
-			if (exact) launch_delta<Exact>(s, k, nb);
-			else launch_delta<Fast>(s, k, nb);
-			s->pos.flip();
+			run_delta(s, k, nb);
 			break;
 		case SPH_PASS_COLLIDE:
 			collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), 1.0f / dt, 1, 0, 0);

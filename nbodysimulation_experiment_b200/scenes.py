@@ -19,7 +19,8 @@ def _domain(nx, spacing):
 
 
 def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mode=_lib.SPH_FP_EXACT, flags=0,
-                relaxation=1.0, device=0, rank=0, world_size=1, capacity=None, near_stiffness=None, **params):
+                relaxation=1.0, device=0, rank=0, world_size=1, capacity=None, near_stiffness=None,
+                solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0, **params):
     """c3 / c4: nx x ny block (default square), 4 boundary planes, dam-break under gravity."""
     ny = nx if ny is None else ny
     width, height = _domain(nx, spacing)
@@ -27,7 +28,8 @@ def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mo
     if capacity is None:
         capacity = n + 1024 if world_size == 1 else int(n / world_size * 1.6) + 65536
     sim = ParticleSimulation(domain_width=width, domain_height=height, cell_size=KERNEL_HEIGHT, max_particles=capacity,
-                             device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size)
+                             device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size,
+                             solver=solver, sweep_capacity=sweep_capacity)
     p = sim.GetParams()
     p.particle_spacing = spacing
     if near_stiffness is not None:

@@ -27,7 +27,8 @@ class ParticleSimulation:
     """One simulation in HBM.  Defaults are the reference's compile-time world (sph.h:18-72)."""
 
     def __init__(self, domain_width=None, domain_height=None, cell_size=None, max_particles=None, device=0,
-                 fp_mode=_lib.SPH_FP_EXACT, flags=0, relaxation=1.0, rank=0, world_size=1, halo_capacity=0):
+                 fp_mode=_lib.SPH_FP_EXACT, flags=0, relaxation=1.0, rank=0, world_size=1, halo_capacity=0,
+                 solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0):
         self._lib = _lib.load()
         cfg = SphConfig()
         self._check(self._lib.sph_config_default(C.byref(cfg)), None)
@@ -43,6 +44,8 @@ class ParticleSimulation:
         cfg.fp_mode = fp_mode
         cfg.flags = flags
         cfg.relaxation = relaxation
+        cfg.solver = solver
+        cfg.sweep_capacity = sweep_capacity
         cfg.rank = rank
         cfg.world_size = world_size
         cfg.halo_capacity = halo_capacity

@@ -249,7 +249,7 @@ static void grid_remove(SphOracle *o, uint64_t i) { /* demo4.cpp:56-76: swap wit
  * order instead, so each cell lists its members by ascending id — the canonical order the GPU's
  * per-cell id ranking produces. */
 void oracle_pass_update_grid(SphOracle *o) {
-	if (o->mode == ORACLE_MODE_JACOBI) {
+	if (o->mode != ORACLE_MODE_GS_INDEX) {
 		size_t ncell = (size_t)o->gridX * o->gridY;
 		for (size_t c = 0; c < ncell; ++c) o->cells[c].count = 0;
 		for (uint64_t i = 0; i < o->n; ++i) grid_insert(o, i);
@@ -444,6 +444,93 @@ static void delta_range_jacobi(SphOracle *o, int64_t s, int64_t e, float dt) {
 	}
 }
 
+/* ---- 9-colour cell Gauss-Seidel (ORACLE_MODE_COLORED) ---------------------------------------
+ * The reference's in-place sweeps (demo4.cpp:223-255) visit particles in index order, which a GPU
+ * cannot do in parallel, and its own multithreaded mode visits them in a racy order.  Cells whose
+ * (cx mod 3, cy mod 3) agree have disjoint 3x3 footprints, so sweeping the nine colours one after
+ * another, cells of a colour in any order, particles of a cell by ascending id, is a legitimate
+ * race-free in-place sweep.  Inside one particle's loop the pair terms are evaluated by 32 "lanes"
+ * (candidate k belongs to lane k mod 32) from the particle's state at loop entry; partners are
+ * updated immediately, the particle's own change is summed per lane, combined by a 5-stage
+ * butterfly and applied at the end - exactly what the CUDA kernel does, so results are bit-equal. */
+static float butterfly_sum(float part[32]) {
+	for (int o = 16; o; o >>= 1) {
+		float next[32];
+		for (int l = 0; l < 32; ++l) next[l] = part[l] + part[l ^ o];
+		memcpy(part, next, sizeof(next));
+	}
+	return part[0];
+}
+
+static inline int color_of(const SphOracle *o, uint64_t i) { return (o->pi[i].cy % 3) * 3 + (o->pi[i].cx % 3); }
+
+static void delta_colored(SphOracle *o, float dt) {
+	const float h = o->params[0], invH = o->params[3];
+	for (int color = 0; color < 9; ++color)
+		for (uint64_t i = 0; i < o->nbrN; ++i) {
+			if (color_of(o, i) != color) continue;
+			Particle *a = &o->p[i];
+			const V2 xi = a->cur;
+			float px[32], py[32];
+			memset(px, 0, sizeof(px));
+			memset(py, 0, sizeof(py));
+			uint64_t b0 = nbr_begin(o, i), e0 = nbr_end(o, i);
+			for (uint64_t k = b0; k < e0; ++k) {
+				Particle *b = &o->p[o->nbr[k]];
+				int lane = (int)((k - b0) & 31u);
+				V2 rij = v2_sub(b->cur, xi);
+				float r2 = v2_dot(rij, rij);
+				if (r2 < (h * h)) {
+					float r = sqrtf(r2);
+					V2 nrm = v2_normalize(rij);
+					float term = 1.0f - r * invH;
+					float d = (dt * dt) * (a->P * term + a->PNear * (term * term)); /* sph.h:492 */
+					V2 half = v2(d * nrm.x * 0.5f, d * nrm.y * 0.5f);
+					b->cur = v2_add(half, b->cur);  /* demo4.cpp:250 */
+					px[lane] = px[lane] - half.x;   /* demo4.cpp:251 */
+					py[lane] = py[lane] - half.y;
+				}
+			}
+			float dx = butterfly_sum(px), dy = butterfly_sum(py);
+			a->cur = v2_add(v2(dx, dy), a->cur);    /* demo4.cpp:253 */
+		}
+}
+
+static void viscosity_colored(SphOracle *o, float dt) {
+	const float h = o->params[0], invH = o->params[3], sigma = o->params[7], beta = o->params[8];
+	for (int color = 0; color < 9; ++color)
+		for (uint64_t i = 0; i < o->nbrN; ++i) {
+			if (color_of(o, i) != color) continue;
+			Particle *a = &o->p[i];
+			const V2 xi = a->cur, vi = a->vel;
+			float px[32], py[32];
+			memset(px, 0, sizeof(px));
+			memset(py, 0, sizeof(py));
+			uint64_t b0 = nbr_begin(o, i), e0 = nbr_end(o, i);
+			for (uint64_t k = b0; k < e0; ++k) {
+				Particle *b = &o->p[o->nbr[k]];
+				int lane = (int)((k - b0) & 31u);
+				V2 rij = v2_sub(b->cur, xi);
+				float r2 = v2_dot(rij, rij);
+				if (r2 < (h * h)) {
+					float r = sqrtf(r2);
+					float q = r * invH;
+					V2 nrm = v2_normalize(rij);
+					float u = v2_dot(v2_sub(vi, b->vel), nrm);
+					if (u > 0.0f) {
+						float f = (1.0f - q) * (sigma * u + beta * (u * u)); /* sph.h:508 */
+						V2 half = v2((f * nrm.x * 0.5f) * dt, (f * nrm.y * 0.5f) * dt); /* demo4.cpp:233 */
+						b->vel = v2_add(half, b->vel);
+						px[lane] = px[lane] - half.x;
+						py[lane] = py[lane] - half.y;
+					}
+				}
+			}
+			float dx = butterfly_sum(px), dy = butterfly_sum(py);
+			a->vel = v2_add(v2(dx, dy), a->vel);
+		}
+}
+
 static void ensure_scratch(SphOracle *o) {
 	if (o->scratchCap < o->n) {
 		o->scratchCap = o->n;
@@ -454,7 +541,9 @@ static void ensure_scratch(SphOracle *o) {
 void oracle_pass_density(SphOracle *o) { run_ranges(o, density_range, 0.0f); }
 
 void oracle_pass_viscosity(SphOracle *o, float dt) {
-	if (o->mode == ORACLE_MODE_JACOBI) {
+	if (o->mode == ORACLE_MODE_COLORED) {
+		viscosity_colored(o, dt);
+	} else if (o->mode == ORACLE_MODE_JACOBI) {
 		ensure_scratch(o);
 		run_ranges(o, viscosity_range_jacobi, dt);
 		for (uint64_t i = 0; i < o->n; ++i) o->p[i].vel = o->scratch[i];
@@ -464,7 +553,9 @@ void oracle_pass_viscosity(SphOracle *o, float dt) {
 }
 
 void oracle_pass_delta(SphOracle *o, float dt) {
-	if (o->mode == ORACLE_MODE_JACOBI) {
+	if (o->mode == ORACLE_MODE_COLORED) {
+		delta_colored(o, dt);
+	} else if (o->mode == ORACLE_MODE_JACOBI) {
 		ensure_scratch(o);
 		run_ranges(o, delta_range_jacobi, dt);
 		for (uint64_t i = 0; i < o->n; ++i) o->p[i].cur = o->scratch[i];

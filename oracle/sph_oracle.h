@@ -27,9 +27,12 @@ enum {
 	ORACLE_MODE_GS_INDEX = 0, /* the reference's semantics: in-place half-weight pair updates in
 	                             particle-index order over neighbour lists in the reference's own
 	                             cell-storage order (demo4.cpp:223-255) */
-	ORACLE_MODE_JACOBI = 1    /* the deterministic per-particle gather the GPU implements: every
+	ORACLE_MODE_JACOBI = 1,   /* the deterministic per-particle gather the GPU implements: every
 	                             pair term evaluated from the pass's input state; candidates walked
 	                             in (dy, dx, ascending particle id) order */
+	ORACLE_MODE_COLORED = 2   /* the reference's in-place half-weight pair updates swept race-free:
+	                             nine cell colours (cx mod 3, cy mod 3), ascending id inside a cell,
+	                             32-lane evaluation of each particle's loop (see sph_oracle.c) */
 };
 
 enum { ORACLE_BODY_PLANE = 1, ORACLE_BODY_CIRCLE = 2, ORACLE_BODY_SEGMENT = 3, ORACLE_BODY_POLYGON = 4 };

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle_lib import MODE_JACOBI, CpuSim, point_solvers
+from oracle_lib import MODE_COLORED, MODE_JACOBI, CpuSim, point_solvers
 
 pytestmark = pytest.mark.gpu
 
@@ -54,12 +54,15 @@ def candidate_sets_from_grid(ids, start, gx, gy, cx, cy):
     return np.concatenate(out) if out else np.zeros(0, np.uint32)
 
 
-# ---- whole steps, reference scenes, GPU exact == oracle gather, bit for bit ---------------------
-@pytest.mark.parametrize("scene,steps,omega", [(0, 8, 1.0), (0, 40, 0.5), (1, 40, 1.0), (2, 64, 1.0), (3, 64, 1.0)])
-def test_scene_steps_bitwise_vs_oracle(pkg, scene, steps, omega):
-    gpu = pkg.ParticleSimulation(relaxation=omega)
+# ---- whole steps, reference scenes, GPU exact == oracle (same solver), bit for bit -----------------
+# solver "gs" = coloured Gauss-Seidel sweeps (default), "gather" = Jacobi gather with relaxation omega
+@pytest.mark.parametrize("scene,steps,solver,omega", [
+    (0, 64, "gs", 1.0), (1, 64, "gs", 1.0), (2, 64, "gs", 1.0), (3, 64, "gs", 1.0),
+    (0, 8, "gather", 1.0), (0, 40, "gather", 0.5), (1, 40, "gather", 1.0), (2, 64, "gather", 1.0), (3, 64, "gather", 1.0)])
+def test_scene_steps_bitwise_vs_oracle(pkg, scene, steps, solver, omega):
+    gpu = pkg.ParticleSimulation(relaxation=omega, solver=pkg.SPH_SOLVER_COLORED_GS if solver == "gs" else pkg.SPH_SOLVER_GATHER)
     gpu.LoadScenario(scene, seed=1)
-    cpu = CpuSim("oracle", mode=MODE_JACOBI, threads=8)
+    cpu = CpuSim("oracle", mode=MODE_COLORED if solver == "gs" else MODE_JACOBI, threads=8)
     cpu.set_relaxation(omega)
     cpu.load_scenario(scene, 1)
     n = cpu.n
@@ -98,14 +101,14 @@ def test_emitter_scenes_bitwise_vs_oracle(pkg, scene):
     """Emitters change N every few steps (host rand() cadence, demo4.cpp:257-284); polygons and a
     circle in scenes 5 and 7.  Runs are sequential because both sides draw from libc rand()."""
     steps = 150
-    gpu = pkg.ParticleSimulation()
+    gpu = pkg.ParticleSimulation()  # default solver: coloured Gauss-Seidel
     gpu.LoadScenario(scene, seed=9)
     for _ in range(steps):
         gpu.Update(DT)
     a = gpu.particles()
     ga = gpu.cell_counts()
     gpu.close()
-    cpu = CpuSim("oracle", mode=MODE_JACOBI)
+    cpu = CpuSim("oracle", mode=MODE_COLORED)
     cpu.load_scenario(scene, 9)
     cpu.advance(DT, steps)
     assert a.shape[0] == cpu.n and cpu.n > 300
@@ -204,12 +207,13 @@ def test_collision_pass_bitwise(pkg):
     gpu.close()
 
 
-def test_viscosity_and_delta_passes_bitwise(pkg):
+@pytest.mark.parametrize("solver", ["gs", "gather"])
+def test_viscosity_and_delta_passes_bitwise(pkg, solver):
     """Per-pass parity from an injected state (a reference dump, mid-splash)."""
     g = np.load(os.path.join(GOLDEN_DIR, "scene1.npz"))
     state = g["state32"]
-    gpu = pkg.ParticleSimulation()
-    cpu = CpuSim("oracle", mode=MODE_JACOBI)
+    gpu = pkg.ParticleSimulation(solver=pkg.SPH_SOLVER_COLORED_GS if solver == "gs" else pkg.SPH_SOLVER_GATHER)
+    cpu = CpuSim("oracle", mode=MODE_COLORED if solver == "gs" else MODE_JACOBI)
     gpu.LoadScenario(1, seed=1)
     cpu.load_scenario(1, 1)
     gpu.put_particles(state)
@@ -223,10 +227,11 @@ def test_viscosity_and_delta_passes_bitwise(pkg):
     gpu.close()
 
 
-def test_fast_mode_close_to_exact(pkg):
+@pytest.mark.parametrize("solver", [0, 1])
+def test_fast_mode_close_to_exact(pkg, solver):
     runs = []
     for mode in (pkg.SPH_FP_EXACT, pkg.SPH_FP_FAST):
-        s = pkg.ParticleSimulation(fp_mode=mode)
+        s = pkg.ParticleSimulation(fp_mode=mode, solver=solver)
         s.LoadScenario(2, seed=1)
         s.Update(DT)
         s.Update(DT)
@@ -255,7 +260,7 @@ def test_hashed_block_bitwise_vs_threaded_oracle(pkg):
     """65 536 particles from the device-side generator; oracle gather mode on 8 threads."""
     from nbodysimulation_experiment_b200 import scenes
 
-    gpu = scenes.fill_block(scenes.block_scene(256, spacing=0.1, gravity=(0.0, -2.0)))
+    gpu = scenes.fill_block(scenes.block_scene(256, spacing=0.1, gravity=(0.0, -2.0), solver=pkg.SPH_SOLVER_GATHER))
     n = gpu.GetParticleCount()
     assert n == 256 * 256
     init = gpu.particles()
@@ -305,3 +310,62 @@ def test_million_particle_invariants(pkg):
     assert st.max_particle_neighbor_count >= st.min_particle_neighbor_count > 0
     gpu.close()
     del hw, hh, cell
+
+
+# ---- the coloured Gauss-Seidel sweeps -------------------------------------------------------------
+@pytest.mark.parametrize("cap", [32, 96, 512])
+def test_colored_sweep_staging_capacity_does_not_change_results(pkg, cap):
+    """Blocks that do not fit the shared-memory staging take the L2 path: same bits either way.
+    Scene 0 has 250-360 candidates per block, so cap=32/96 forces the L2 path everywhere."""
+    gpu = pkg.ParticleSimulation(sweep_capacity=cap)
+    gpu.LoadScenario(0, seed=1)
+    cpu = CpuSim("oracle", mode=MODE_COLORED)
+    cpu.load_scenario(0, 1)
+    for _ in range(6):
+        gpu.Update(DT)
+        cpu.advance(DT)
+    assert_bits_equal(gpu.particles(), cpu.particles(), f"sweep capacity {cap}")
+    gpu.close()
+    cpu.close()
+
+
+def test_colored_block_bitwise_vs_oracle(pkg):
+    """16 384 particles from the device-side generator, dense regime (spacing h/6), 12 steps."""
+    from nbodysimulation_experiment_b200 import scenes
+
+    gpu = scenes.fill_block(scenes.block_scene(128, spacing=0.05, gravity=(0.0, -8.3)))
+    n = gpu.GetParticleCount()
+    assert n == 128 * 128
+    init = gpu.particles()
+    w, h = gpu.scene["width"], gpu.scene["height"]
+    cpu = CpuSim("oracle", width=w, height=h, cell=scenes.KERNEL_HEIGHT, mode=MODE_COLORED)
+    cpu.put_params(gpu.params_array())
+    cpu.set_gravity(0.0, float(np.float32(-8.3)))
+    for nx, ny, d in ((0.0, 1.0, -h / 2), (0.0, -1.0, -h / 2), (1.0, 0.0, -w / 2), (-1.0, 0.0, -w / 2)):
+        cpu.add_plane(nx, ny, float(np.float32(d)))
+    for x, y in init[:, 0:2]:
+        cpu.add_particle(float(x), float(y), 0.0, 0.0)
+    for _ in range(12):
+        gpu.Update(DT)
+        cpu.advance(DT)
+    assert_bits_equal(gpu.particles(), cpu.particles(), "16k dense block after 12 steps")
+    gpu.close()
+    cpu.close()
+
+
+def test_colored_solver_tracks_reference_energy(pkg):
+    """Statistical parity with the REFERENCE's own single-thread run of its default scene (golden
+    dump): the coloured sweep is a different, equally legitimate in-place order, so trajectories
+    differ particle by particle (like the reference's MT vs ST runs) but the bulk must agree."""
+    g = np.load(os.path.join(GOLDEN_DIR, "scene0.npz"))
+    gpu = pkg.ParticleSimulation()
+    gpu.LoadScenario(0, seed=1)
+    assert_bits_equal(gpu.particles(), g["init"], "initial state equals the reference's")
+    for _ in range(8):
+        gpu.Update(DT)
+    a, b = gpu.particles(), g["state8"]
+    ke = lambda p: 0.5 * float((p[:, 6:8].astype(np.float64) ** 2).sum())
+    assert abs(ke(a) / ke(b) - 1.0) < 0.5
+    assert np.abs(a[:, 0:2].mean(0) - b[:, 0:2].mean(0)).max() < 2e-2   # centre of mass
+    assert abs(a[:, 8].mean() / b[:, 8].mean() - 1.0) < 0.05            # mean density
+    gpu.close()
