@@ -76,7 +76,9 @@ typedef struct SphConfig {
 	/* y-strip decomposition; world_size = 1 for a single GPU */
 	int32_t rank;
 	int32_t world_size;
-	uint64_t halo_capacity;  /* particles per direction per step the exchange buffers hold (0 = auto) */
+	uint64_t halo_capacity;  /* particles per direction per step the exchange buffers hold (0 = max_particles/4) */
+	int32_t halo_rows;       /* ghost rows kept on each side of the strip (0 = 13) */
+	int32_t reserved0;
 } SphConfig;
 
 /* SPHParameters, sph.h:77-87, same field order. */
@@ -203,6 +205,11 @@ int sph_comm_init(SphHandle h, const uint8_t id128[128]);
 /* rows [row_begin, row_end) of the grid this rank owns (even split of occupied rows at init) */
 int sph_set_strip(SphHandle h, int32_t row_begin, int32_t row_end);
 int sph_get_strip(SphHandle h, int32_t *row_begin, int32_t *row_end);
+/* The particles this rank owns, compacted in arbitrary order: creation ids, ParticleData records
+ * (as sph_read_particles), and/or Render()'s positions and colours.  Any output pointer may be NULL;
+ * *count receives the number of owned particles.  Works for world_size = 1 too. */
+int sph_read_owned(SphHandle h, uint32_t *ids, void *records, size_t record_stride, void *positions, size_t pos_stride,
+                   void *colors, size_t color_stride, uint64_t *count);
 
 #ifdef __cplusplus
 }

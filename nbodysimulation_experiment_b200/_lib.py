@@ -41,6 +41,8 @@ class SphConfig(C.Structure):
         ("rank", c_i32),
         ("world_size", c_i32),
         ("halo_capacity", c_u64),
+        ("halo_rows", c_i32),
+        ("reserved0", c_i32),
     ]
 
 
@@ -114,6 +116,7 @@ SIGNATURES = {
     "sph_comm_init": (C.c_int, [c_vp, c_vp]),
     "sph_set_strip": (C.c_int, [c_vp, c_i32, c_i32]),
     "sph_get_strip": (C.c_int, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "sph_read_owned": (C.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_sz, c_vp, c_sz, C.POINTER(c_u64)]),
 }
 
 _lib = None

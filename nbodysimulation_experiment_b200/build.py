@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
     "-shared",
+    "-ldl",
 ]
 
 

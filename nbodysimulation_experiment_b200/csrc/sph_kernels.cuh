@@ -121,45 +121,145 @@ __global__ void __launch_bounds__(SPH_THREADS) viscosity_kernel(GridDesc g, Pair
 // ---- phases 3+4a: predict, cell key, histogram (demo4.cpp:330-356) -------------------------
 // prev = x; x += v*dt; cell = SPHComputeCellIndex(x); rank = cellCount[cell]++ (warp-aggregated).
 // With doPredict = 0 only the grid part runs (sph_run_pass(GRID) / state injection).
-__global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, Counters *__restrict__ ctr, float2 *__restrict__ pos,
+// Multi-GPU (y-strips): a rank advances every particle it holds, but only the ones
+// it OWNED on the previous grid are authoritative.  After predict each of those is (a) kept if its
+// new row is inside the local window [rowLo,rowHi) = owned rows +- halo, (b) copied to the lower /
+// upper neighbour if the row is inside that neighbour's window.  Stale ghost copies are dropped;
+// the neighbour sends fresh ones every step.  One exchange per step carries migration and halo.
+struct HaloRecord { // what a neighbour needs to file a particle into this step's grid
+	float2 pos, prev;
+	uint32_t id, pad;
+};
+struct HaloBuffer {
+	uint32_t count, pad[7]; // 32-byte header
+	// HaloRecord records[capacity] follow
+};
+__device__ __forceinline__ HaloRecord *halo_records(HaloBuffer *b) { return reinterpret_cast<HaloRecord *>(b + 1); }
+__device__ __forceinline__ const HaloRecord *halo_records(const HaloBuffer *b) { return reinterpret_cast<const HaloRecord *>(b + 1); }
+
+struct StripDesc {
+	int32_t rank, world, halo;  // halo rows on each side
+	uint32_t haloCap;           // records per HaloBuffer
+	HaloBuffer *sendDown, *sendUp;
+};
+
+// shared tail of predict_key / unpack: claim a rank inside the cell, one atomic per distinct cell per warp
+__device__ __forceinline__ uint32_t claim_cell_rank(uint32_t key, bool valid, uint32_t *__restrict__ cellCount) {
+	const uint32_t peers = __match_any_sync(0xffffffffu, key);
+	const int leader = __ffs(peers) - 1;
+	uint32_t base = 0;
+	if (valid && (int)lane_id() == leader) base = atomicAdd(&cellCount[key], (uint32_t)__popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + (uint32_t)__popc(peers & ((1u << lane_id()) - 1u));
+}
+
+__global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, StripDesc sd, Counters *__restrict__ ctr, float2 *__restrict__ pos,
                                                                  float2 *__restrict__ prev, const float2 *__restrict__ vel,
+                                                                 const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellOld,
                                                                  uint32_t *__restrict__ cellNew, uint32_t *__restrict__ rank,
                                                                  uint32_t *__restrict__ cellCount, float dt, int doPredict) {
-	const uint32_t n = ctr->n;
+	const uint32_t n = ctr->n, nSorted = ctr->nSorted;
 	SPH_WARP_LOOP(i, n) {
 		const bool in = i < n;
 		uint32_t key = 0xFFFFFF00u | lane_id(); // unique per lane: never matches
 		uint32_t packed = SPH_KEY_NONE;
 		if (in) {
 			float2 p = pos[i];
+			float2 q = prev[i];
 			if (doPredict) {
 				const float2 v = vel[i];
+				q = p;
 				prev[i] = p;
 				p.x = __fadd_rn(__fmul_rn(v.x, dt), p.x);
 				p.y = __fadd_rn(__fmul_rn(v.y, dt), p.y);
 				pos[i] = p;
 			}
-			int cx, cy;
-			cell_of(g, p, cx, cy);
-			if (cy >= g.rowLo && cy < g.rowHi) {
-				key = (uint32_t)(cy - g.rowLo) * (uint32_t)g.gx + (uint32_t)cx;
-				packed = pack_cell(cx, cy);
-			} else {
-				atomicAdd(&ctr->lost, 1u);
+			bool authoritative = true;
+			if (sd.world > 1 && i < nSorted) { // ghosts of the previous grid are not ours to file
+				const int rowOld = (int)(cellOld[i] >> 16);
+				authoritative = rowOld >= g.ownLo && rowOld < g.ownHi;
+			}
+			if (authoritative) {
+				int cx, cy;
+				cell_of(g, p, cx, cy);
+				bool placed = false;
+				if (cy >= g.rowLo && cy < g.rowHi) {
+					key = (uint32_t)(cy - g.rowLo) * (uint32_t)g.gx + (uint32_t)cx;
+					packed = pack_cell(cx, cy);
+					placed = true;
+				}
+				if (sd.world > 1) {
+					HaloRecord rec;
+					rec.pos = p;
+					rec.prev = q;
+					rec.id = id[i];
+					rec.pad = 0;
+					if (sd.rank > 0 && cy < g.ownLo + sd.halo) {
+						const uint32_t at = atomicAdd(&sd.sendDown->count, 1u);
+						if (at < sd.haloCap) halo_records(sd.sendDown)[at] = rec;
+						else atomicOr(&ctr->overflow, 2u);
+						placed = true;
+					}
+					if (sd.rank + 1 < sd.world && cy >= g.ownHi - sd.halo) {
+						const uint32_t at = atomicAdd(&sd.sendUp->count, 1u);
+						if (at < sd.haloCap) halo_records(sd.sendUp)[at] = rec;
+						else atomicOr(&ctr->overflow, 2u);
+						placed = true;
+					}
+				}
+				if (!placed) atomicAdd(&ctr->lost, 1u);
 			}
 		}
-		// one atomic per distinct cell per warp
-		const uint32_t peers = __match_any_sync(0xffffffffu, key);
-		const int leader = __ffs(peers) - 1;
-		uint32_t base = 0;
-		if (packed != SPH_KEY_NONE && (int)lane_id() == leader) base = atomicAdd(&cellCount[key], (uint32_t)__popc(peers));
-		base = __shfl_sync(0xffffffffu, base, leader);
+		const uint32_t r = claim_cell_rank(key, packed != SPH_KEY_NONE, cellCount);
 		if (in) {
 			cellNew[i] = packed;
-			rank[i] = base + (uint32_t)__popc(peers & ((1u << lane_id()) - 1u));
+			rank[i] = r;
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctr->nIn = n;
+}
+
+// append the records received from one neighbour behind the local particles and file them
+__global__ void __launch_bounds__(SPH_THREADS) unpack_kernel(GridDesc g, Counters *__restrict__ ctr, const HaloBuffer *__restrict__ in, uint32_t haloCap,
+                                                            uint32_t capacity, uint32_t baseOffset, const HaloBuffer *__restrict__ before,
+                                                            float2 *__restrict__ pos, float2 *__restrict__ prev, uint32_t *__restrict__ id,
+                                                            uint32_t *__restrict__ cellNew, uint32_t *__restrict__ rank, uint32_t *__restrict__ cellCount) {
+	// records land at [n + (count of the buffer unpacked before this one), ...)
+	const uint32_t count = min(in->count, haloCap);
+	const uint32_t first = ctr->n + baseOffset + (before ? min(before->count, haloCap) : 0u);
+	SPH_WARP_LOOP(k, count) {
+		const bool ok = k < count && first + k < capacity;
+		uint32_t key = 0xFFFFFF00u | lane_id();
+		uint32_t packed = SPH_KEY_NONE;
+		if (ok) {
+			const HaloRecord rec = halo_records(in)[k];
+			int cx, cy;
+			cell_of(g, rec.pos, cx, cy);
+			if (cy >= g.rowLo && cy < g.rowHi) {
+				key = (uint32_t)(cy - g.rowLo) * (uint32_t)g.gx + (uint32_t)cx;
+				packed = pack_cell(cx, cy);
+			}
+			pos[first + k] = rec.pos;
+			prev[first + k] = rec.prev;
+			id[first + k] = rec.id;
+		} else if (k < count) {
+			atomicOr(&ctr->overflow, 1u);
+		}
+		const uint32_t r = claim_cell_rank(key, packed != SPH_KEY_NONE, cellCount);
+		if (ok) {
+			cellNew[first + k] = packed;
+			rank[first + k] = r;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		const uint32_t end = min(first + count, capacity);
+		atomicMax(&ctr->nIn, end);
+	}
+}
+
+__global__ void reset_halo_kernel(HaloBuffer *a, HaloBuffer *b) {
+	if (a) a->count = 0;
+	if (b) b->count = 0;
 }
 
 // ---- phase 4b: exclusive scan of the cell histogram ----------------------------------------
@@ -600,6 +700,54 @@ __global__ void __launch_bounds__(SPH_THREADS) gather_records_kernel(const Count
 		r.P = pr.x;
 		r.PNear = pr.y;
 		out[k] = r;
+	}
+}
+
+// multi-GPU readback: the particles this rank OWNS (row of their cell inside the strip), compacted
+// in arbitrary order together with their ids; colours as in render_kernel
+__global__ void __launch_bounds__(SPH_THREADS) gather_owned_kernel(GridDesc g, const Counters *__restrict__ ctr, const uint32_t *__restrict__ id,
+                                                                  const uint32_t *__restrict__ cellOf, const float2 *__restrict__ pos,
+                                                                  const float2 *__restrict__ prev, const float2 *__restrict__ vel,
+                                                                  const float2 *__restrict__ acc, const float2 *__restrict__ dens,
+                                                                  const float2 *__restrict__ press, float restDensity, uint32_t *__restrict__ outCount,
+                                                                  uint32_t *__restrict__ outId, ParticleRecord *__restrict__ outRec,
+                                                                  float2 *__restrict__ outPos, float4 *__restrict__ outColor) {
+	const uint32_t n = ctr->n, nSorted = ctr->nSorted;
+	SPH_WARP_LOOP(i, n) {
+		bool own = i < n;
+		if (own && i < nSorted) {
+			const int row = (int)(cellOf[i] >> 16);
+			own = row >= g.ownLo && row < g.ownHi;
+		}
+		const uint32_t mask = __ballot_sync(0xffffffffu, own);
+		if (!mask) continue;
+		uint32_t base = 0;
+		const int leader = __ffs(mask) - 1;
+		if ((int)lane_id() == leader) base = atomicAdd(outCount, (uint32_t)__popc(mask));
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if (!own) continue;
+		const uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
+		outId[k] = id[i];
+		const float2 d = dens[i], pr = press[i], v = vel[i];
+		if (outRec) {
+			ParticleRecord r;
+			r.cur = pos[i];
+			r.prev = prev[i];
+			r.acc = acc[i];
+			r.vel = v;
+			r.rho = d.x;
+			r.rhoNear = d.y;
+			r.P = pr.x;
+			r.PNear = pr.y;
+			outRec[k] = r;
+		}
+		if (outPos) {
+			const float rr = __fdiv_rn(pr.x, -10.0f);
+			const float gg = __fdiv_rn(d.x, restDensity);
+			const float bb = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))), 10.0f);
+			outPos[k] = pos[i];
+			outColor[k] = make_float4(fmaxf(fminf(rr, 1.0f), 0.0f), fmaxf(fminf(gg, 1.0f), 0.0f), fmaxf(fminf(bb, 1.0f), 0.0f), 1.0f);
+		}
 	}
 }
 

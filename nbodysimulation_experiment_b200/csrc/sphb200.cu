@@ -7,6 +7,7 @@
 #include "../../include/sphb200.h"
 #include "sph_kernels.cuh"
 
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -36,6 +37,52 @@ struct HostEmitter { // Demo4::ParticleEmitter, demo4.h:123-133
 	float px, py, dx, dy, radius, speed, rate, duration, elapsed, totalElapsed;
 	int active;
 };
+
+// ---- NCCL, bound at run time (no link-time dependency: single-GPU users never load it) -------
+// Minimal declarations of the stable NCCL 2.x C API (nccl.h:37-38,146,160,181,215,442,461,493,503).
+typedef struct ncclComm *NcclComm;
+typedef struct { char internal[128]; } NcclUniqueId;
+struct NcclApi {
+	void *lib = nullptr;
+	int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+	int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+	int (*CommDestroy)(NcclComm) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+	int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	std::string error;
+	bool load() {
+		if (lib) return true;
+		for (const char *name : { "libnccl.so.2", "libnccl.so" }) {
+			lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (lib) break;
+		}
+		if (!lib) {
+			error = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+			return false;
+		}
+#define BIND(field, sym)                                                    \
+	field = reinterpret_cast<decltype(field)>(dlsym(lib, sym));             \
+	if (!field) {                                                           \
+		error = std::string("NCCL symbol missing: ") + sym;                 \
+		return false;                                                       \
+	}
+		BIND(GetUniqueId, "ncclGetUniqueId")
+		BIND(CommInitRank, "ncclCommInitRank")
+		BIND(CommDestroy, "ncclCommDestroy")
+		BIND(GetErrorString, "ncclGetErrorString")
+		BIND(Send, "ncclSend")
+		BIND(Recv, "ncclRecv")
+		BIND(GroupStart, "ncclGroupStart")
+		BIND(GroupEnd, "ncclGroupEnd")
+#undef BIND
+		return true;
+	}
+};
+NcclApi g_nccl;
+constexpr int kNcclUint8 = 1; // ncclUint8, nccl.h:279
 
 enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DENSITY, PH_DELTA, PH_COLLIDE, PH_EXCHANGE, PH_COUNT };
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
@@ -74,7 +121,14 @@ struct SphSim {
 	float4 *dRenderCol = nullptr;
 	int2 *dCellXY = nullptr;
 
-	uint64_t hostN = 0;        // particles this rank holds (exact on one GPU)
+	// y-strip decomposition
+	StripDesc strip = {};
+	HaloBuffer *sendBuf[2] = { nullptr, nullptr }, *recvBuf[2] = { nullptr, nullptr }; // [0] = lower neighbour, [1] = upper
+	size_t haloBytes = 0;
+	NcclComm comm = nullptr;
+	uint32_t *dOwnedCount = nullptr, *dOwnedIds = nullptr;
+
+	uint64_t hostN = 0;        // particles this rank holds (exact on one GPU; an upper bound on strips)
 	uint64_t nextId = 0;       // creation counter
 	uint32_t accFrom = 0xFFFFFFFFu; // first array slot whose acceleration is live
 
@@ -248,13 +302,49 @@ void record_phase(SphSim *s, int idx) {
 }
 
 // ---- the grid build shared by sph_step and sph_run_pass(GRID) ------------------------------
+// migration + halo in one neighbour exchange (fixed-size messages, count in the header), then file
+// what arrived behind the local particles
+int exchange_halos(SphSim *s) {
+	const StripDesc &sd = s->strip;
+	if (!s->comm) return fail(s, SPH_ERR_STATE, "sph_comm_init was not called on this multi-GPU handle");
+	NcclApi &nc = g_nccl;
+	int rc = nc.GroupStart();
+	if (rc == 0 && sd.rank > 0) {
+		rc = nc.Send(s->sendBuf[0], s->haloBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->recvBuf[0], s->haloBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+	}
+	if (rc == 0 && sd.rank + 1 < sd.world) {
+		rc = nc.Send(s->sendBuf[1], s->haloBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->recvBuf[1], s->haloBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+	}
+	const int rcEnd = nc.GroupEnd();
+	if (rc == 0) rc = rcEnd;
+	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL exchange failed: %s", nc.GetErrorString(rc));
+	const unsigned nb = blocks_for(sd.haloCap);
+	const GridDesc &g = s->grid;
+	if (sd.rank > 0)
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[0], sd.haloCap, s->capacity, 0u, nullptr, s->pos.in(), s->prev.in(), s->id.in(),
+		                                                s->cellNew, s->rank, s->cellCount);
+	if (sd.rank + 1 < sd.world)
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[1], sd.haloCap, s->capacity, 0u, sd.rank > 0 ? s->recvBuf[0] : nullptr, s->pos.in(),
+		                                                s->prev.in(), s->id.in(), s->cellNew, s->rank, s->cellCount);
+	CU(s, cudaGetLastError());
+	return SPH_OK;
+}
+
 int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed) {
 	const GridDesc &g = s->grid;
 	const unsigned nb = blocks_for(s->hostN);
 	CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
-	predict_key_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->cellNew, s->rank, s->cellCount, dt,
-	                                                      doPredict ? 1 : 0);
+	if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
+	predict_key_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
+	                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
 	if (timed) record_phase(s, PH_PREDICT + 1);
+	if (s->strip.world > 1) {
+		int rc = exchange_halos(s);
+		if (rc != SPH_OK) return rc;
+	}
+	if (timed) record_phase(s, PH_EXCHANGE + 1);
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
 	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
@@ -324,6 +414,36 @@ int run_viscosity(SphSim *s, const PairParams &k, unsigned nb) {
 template <class M>
 void launch_delta(SphSim *s, const PairParams &k, unsigned nb) {
 	delta_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->press.in(), s->cellOf.in(), s->cellStart, s->pos.out());
+}
+
+constexpr int kDefaultHaloRows = 13; // DESIGN.md "multi-GPU": 1 (density) + 6 (displacement sweep) + 6 (next viscosity sweep)
+
+// (re)allocates everything sized by the local window of grid rows
+int configure_strip(SphSim *s, int ownLo, int ownHi) {
+	GridDesc &g = s->grid;
+	if (ownLo < 0 || ownHi > g.gy || ownLo >= ownHi) return fail(s, SPH_ERR_INVALID, "strip rows [%d,%d) outside the grid (0..%d)", ownLo, ownHi, g.gy);
+	const int world = s->strip.world, rank = s->strip.rank, halo = s->strip.halo;
+	if (world > 1 && rank > 0 && rank + 1 < world && ownHi - ownLo < halo)
+		return fail(s, SPH_ERR_INVALID, "interior strip of %d rows is thinner than the %d-row halo", ownHi - ownLo, halo);
+	g.ownLo = ownLo;
+	g.ownHi = ownHi;
+	g.rowLo = world > 1 ? std::max(0, ownLo - halo) : 0;
+	g.rowHi = world > 1 ? std::min(g.gy, ownHi + halo) : g.gy;
+	if (world == 1 && (ownLo != 0 || ownHi != g.gy)) return fail(s, SPH_ERR_INVALID, "a single-GPU simulation owns the whole grid");
+	g.nCells = (uint32_t)(g.rowHi - g.rowLo) * (uint32_t)g.gx;
+	cudaFree(s->cellCount);
+	cudaFree(s->cellStart);
+	cudaFree(s->tileSums);
+	cudaFree(s->colorList);
+	s->cellCount = s->cellStart = s->tileSums = s->colorList = nullptr;
+	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
+	CU(s, cudaMalloc(&s->cellCount, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMemset(s->cellStart, 0, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
+	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
+	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
+	return SPH_OK;
 }
 
 int run_delta(SphSim *s, const PairParams &k, unsigned nb) {
@@ -436,7 +556,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	}
 	g.rowLo = g.ownLo = 0;
 	g.rowHi = g.ownHi = g.gy;
-	g.nCells = (uint32_t)g.gx * (uint32_t)g.gy;
+	g.nCells = 0;
 	s->capacity = (uint32_t)cfg->max_particles;
 
 #define CUC(call)                                                                                        \
@@ -466,15 +586,35 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	CUC(cudaMalloc(&s->cellNew, cap * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->rank, cap * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->slotId, cap * sizeof(uint32_t)));
-	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
-	CUC(cudaMalloc(&s->cellCount, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CUC(cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CUC(cudaMemset(s->cellStart, 0, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CUC(cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
-	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
 	CUC(cudaMalloc(&s->colorCount, 16 * sizeof(uint32_t)));
 	CUC(cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
-	CUC(cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
+	s->strip.rank = cfg->rank;
+	s->strip.world = cfg->world_size;
+	s->strip.halo = cfg->halo_rows > 0 ? cfg->halo_rows : kDefaultHaloRows;
+	{
+		// default strips: an even split of the grid rows; sph_set_strip rebalances before particles are added
+		const int lo = (int)((int64_t)g.gy * cfg->rank / cfg->world_size), hi = (int)((int64_t)g.gy * (cfg->rank + 1) / cfg->world_size);
+		int rcs = configure_strip(s, lo, hi);
+		if (rcs != SPH_OK) {
+			g_createError = s->err;
+			sph_destroy(s);
+			return rcs;
+		}
+	}
+	if (cfg->world_size > 1) {
+		s->strip.haloCap = (uint32_t)(cfg->halo_capacity ? cfg->halo_capacity : std::max<uint64_t>(cap / 4, 4096));
+		s->haloBytes = sizeof(HaloBuffer) + (size_t)s->strip.haloCap * sizeof(HaloRecord);
+		for (int d = 0; d < 2; ++d) {
+			CUC(cudaMalloc(&s->sendBuf[d], s->haloBytes));
+			CUC(cudaMalloc(&s->recvBuf[d], s->haloBytes));
+			CUC(cudaMemset(s->sendBuf[d], 0, sizeof(HaloBuffer)));
+			CUC(cudaMemset(s->recvBuf[d], 0, sizeof(HaloBuffer)));
+		}
+		s->strip.sendDown = s->sendBuf[0];
+		s->strip.sendUp = s->sendBuf[1];
+		s->hostN = cap; // launch bound: the live count is only known on the device
+	}
+	CUC(cudaMalloc(&s->dOwnedCount, sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->dBodies, kMaxBodies * sizeof(DevBody)));
 	for (auto &e : s->phaseEv) CUC(cudaEventCreate(&e));
 	for (auto &e : s->marks) CUC(cudaEventCreate(&e));
@@ -509,6 +649,13 @@ int sph_destroy(SphHandle s) {
 	cudaFree(s->dRenderPos);
 	cudaFree(s->dRenderCol);
 	cudaFree(s->dCellXY);
+	for (int d = 0; d < 2; ++d) {
+		cudaFree(s->sendBuf[d]);
+		cudaFree(s->recvBuf[d]);
+	}
+	cudaFree(s->dOwnedCount);
+	cudaFree(s->dOwnedIds);
+	if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
 	cudaFree(s->dCtr);
 	if (s->hCtr) cudaFreeHost(s->hCtr);
 	for (auto &e : s->phaseEv)
@@ -609,7 +756,7 @@ int sph_body_count(SphHandle s, size_t *out) {
 // ---- particles -------------------------------------------------------------------------------
 int sph_clear_particles(SphHandle s) {
 	CHECK_HANDLE(s);
-	s->hostN = 0;
+	s->hostN = s->cfg.world_size > 1 ? s->capacity : 0;
 	s->nextId = 0;
 	s->accFrom = 0xFFFFFFFFu;
 	s->steppedOnce = false;
@@ -699,10 +846,10 @@ int sph_add_volume_hashed(SphHandle s, float cx, float cy, float fx, float fy, i
 	CU(s, cudaMemcpyAsync(s->hCtr, s->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, s->stream));
 	CU(s, cudaStreamSynchronize(s->stream));
 	if (s->hCtr->overflow & 1u) return fail(s, SPH_ERR_CAPACITY, "particle capacity %u exceeded by sph_add_volume_hashed", s->capacity);
-	s->accFrom = std::min<uint32_t>(s->accFrom, (uint32_t)s->hostN);
-	s->hostN = s->hCtr->n;
+	s->accFrom = s->cfg.world_size > 1 ? 0u : std::min<uint32_t>(s->accFrom, (uint32_t)s->hostN);
+	if (s->cfg.world_size == 1) s->hostN = s->hCtr->n;
 	s->nextId += total;
-	grow_count_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, (uint32_t)s->hostN);
+	grow_count_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, s->hCtr->n);
 	CU(s, cudaGetLastError());
 	return SPH_OK;
 }
@@ -717,6 +864,7 @@ int sph_add_emitter(SphHandle s, float px, float py, float dx, float dy, float r
 
 int sph_local_particle_count(SphHandle s, uint64_t *out) {
 	CHECK_HANDLE(s);
+	if (s->cfg.world_size > 1) return sph_read_owned(s, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, out);
 	if (out) *out = s->hostN;
 	return SPH_OK;
 }
@@ -872,7 +1020,8 @@ extern "C" int sph_load_scenario(SphHandle s, int idx, int seed) {
 int sph_step(SphHandle s, float dt) {
 	CHECK_HANDLE(s);
 	if (!(dt > 0.0f)) return fail(s, SPH_ERR_INVALID, "dt must be > 0");
-	if (s->cfg.world_size > 1) return fail(s, SPH_ERR_STATE, "multi-GPU stepping is not wired in this build");
+	if (s->cfg.world_size > 1 && !s->comm) return fail(s, SPH_ERR_STATE, "call sph_comm_init before stepping a multi-GPU handle");
+	if (s->cfg.world_size > 1 && !s->emitters.empty()) return fail(s, SPH_ERR_STATE, "emitters are single-GPU");
 	if (!s->emitters.empty()) {
 		int rc = update_emitters(s, dt);
 		if (rc != SPH_OK) return rc;
@@ -902,17 +1051,18 @@ int sph_step(SphHandle s, float dt) {
 	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1);
 	commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
 	record_phase(s, PH_COLLIDE + 1);
-	if (s->cfg.flags & SPH_FLAG_PHASE_TIMING) cudaEventRecord(s->phaseEv[PH_COUNT], s->stream);
 	CU(s, cudaGetLastError());
 	s->steps++;
 	s->steppedOnce = true;
 
 	if (s->cfg.flags & SPH_FLAG_PHASE_TIMING) {
-		CU(s, cudaEventSynchronize(s->phaseEv[PH_COUNT]));
+		// event k+1 closes phase k; the exchange sits between predict and scan, so its event (index
+		// PH_EXCHANGE+1) is the one that opens the scan
+		CU(s, cudaEventSynchronize(s->phaseEv[PH_COLLIDE + 1]));
+		const int open[PH_COUNT] = { 0, PH_INTEGRATE + 1, PH_VISCOSITY + 1, PH_EXCHANGE + 1, PH_SCAN + 1, PH_REORDER + 1, PH_DENSITY + 1, PH_DELTA + 1, PH_PREDICT + 1 };
 		for (int p = 0; p < PH_COUNT; ++p) {
 			float ms = 0.0f;
-			if (p == PH_EXCHANGE) continue;
-			cudaEventElapsedTime(&ms, s->phaseEv[p], s->phaseEv[p + 1]);
+			cudaEventElapsedTime(&ms, s->phaseEv[open[p]], s->phaseEv[p + 1]);
 			s->phaseMs[p] += ms;
 		}
 		s->phaseSteps++;
@@ -1139,19 +1289,67 @@ int sph_elapsed_ms(SphHandle s, int a, int b, float *ms) {
 
 // ---- multi-GPU plumbing: not wired in this build ----------------------------------------------------
 int sph_comm_unique_id(uint8_t id128[128]) {
-	(void)id128;
-	return SPH_ERR_STATE;
+	if (!id128) return SPH_ERR_INVALID;
+	if (!g_nccl.load()) return fail(nullptr, SPH_ERR_COMM, "%s", g_nccl.error.c_str());
+	NcclUniqueId id;
+	const int rc = g_nccl.GetUniqueId(&id);
+	if (rc != 0) return fail(nullptr, SPH_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+	memcpy(id128, id.internal, 128);
+	return SPH_OK;
 }
 int sph_comm_init(SphHandle s, const uint8_t id128[128]) {
 	CHECK_HANDLE(s);
-	(void)id128;
-	return fail(s, SPH_ERR_STATE, "multi-GPU exchange is not wired in this build");
+	if (!id128) return fail(s, SPH_ERR_INVALID, "null id");
+	if (s->cfg.world_size < 2) return fail(s, SPH_ERR_STATE, "sph_comm_init needs world_size > 1");
+	if (s->comm) return fail(s, SPH_ERR_STATE, "communicator already initialised");
+	if (!g_nccl.load()) return fail(s, SPH_ERR_COMM, "%s", g_nccl.error.c_str());
+	NcclUniqueId id;
+	memcpy(id.internal, id128, 128);
+	CU(s, cudaSetDevice(s->cfg.device));
+	const int rc = g_nccl.CommInitRank(&s->comm, s->cfg.world_size, id, s->cfg.rank);
+	if (rc != 0) {
+		s->comm = nullptr;
+		return fail(s, SPH_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+	}
+	return SPH_OK;
 }
 int sph_set_strip(SphHandle s, int32_t rowBegin, int32_t rowEnd) {
 	CHECK_HANDLE(s);
-	(void)rowBegin;
-	(void)rowEnd;
-	return fail(s, SPH_ERR_STATE, "multi-GPU exchange is not wired in this build");
+	if (s->nextId != 0) return fail(s, SPH_ERR_STATE, "set the strip before adding particles");
+	CU(s, cudaStreamSynchronize(s->stream));
+	return configure_strip(s, rowBegin, rowEnd);
+}
+
+// the particles this rank owns, compacted (arbitrary order) with their creation ids; any output may be NULL
+int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, void *positions, size_t posStride, void *colors, size_t colStride,
+                   uint64_t *count) {
+	CHECK_HANDLE(s);
+	if ((records && recStride < sizeof(ParticleRecord)) || (positions && posStride < sizeof(float2)) || (colors && colStride < sizeof(float4)))
+		return fail(s, SPH_ERR_INVALID, "stride too small");
+	const size_t cap = s->capacity;
+	if (!s->dOwnedIds) CU(s, cudaMalloc(&s->dOwnedIds, cap * sizeof(uint32_t)));
+	if (records && !s->dRecords) CU(s, cudaMalloc(&s->dRecords, cap * sizeof(ParticleRecord)));
+	if ((positions || colors) && !s->dRenderPos) {
+		CU(s, cudaMalloc(&s->dRenderPos, cap * sizeof(float2)));
+		CU(s, cudaMalloc(&s->dRenderCol, cap * sizeof(float4)));
+	}
+	CU(s, cudaMemsetAsync(s->dOwnedCount, 0, sizeof(uint32_t), s->stream));
+	gather_owned_kernel<<<blocks_for(s->hostN), SPH_THREADS, 0, s->stream>>>(s->grid, s->dCtr, s->id.in(), s->cellOf.in(), s->pos.in(), s->prev.in(), s->vel.in(),
+	                                                                       s->acc.in(), s->dens.in(), s->press.in(), s->params.rest_density, s->dOwnedCount,
+	                                                                       s->dOwnedIds, records ? s->dRecords : nullptr,
+	                                                                       (positions || colors) ? s->dRenderPos : nullptr, s->dRenderCol);
+	CU(s, cudaGetLastError());
+	uint32_t n = 0;
+	CU(s, cudaMemcpyAsync(&n, s->dOwnedCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+	CU(s, cudaStreamSynchronize(s->stream));
+	if (count) *count = n;
+	if (n == 0) return SPH_OK;
+	if (ids) CU(s, cudaMemcpyAsync(ids, s->dOwnedIds, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+	if (records) CU(s, cudaMemcpy2DAsync(records, recStride, s->dRecords, sizeof(ParticleRecord), sizeof(ParticleRecord), n, cudaMemcpyDeviceToHost, s->stream));
+	if (positions) CU(s, cudaMemcpy2DAsync(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost, s->stream));
+	if (colors) CU(s, cudaMemcpy2DAsync(colors, colStride, s->dRenderCol, sizeof(float4), sizeof(float4), n, cudaMemcpyDeviceToHost, s->stream));
+	CU(s, cudaStreamSynchronize(s->stream));
+	return SPH_OK;
 }
 int sph_get_strip(SphHandle s, int32_t *rowBegin, int32_t *rowEnd) {
 	CHECK_HANDLE(s);

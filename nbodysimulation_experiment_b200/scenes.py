@@ -20,16 +20,16 @@ def _domain(nx, spacing):
 
 def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mode=_lib.SPH_FP_EXACT, flags=0,
                 relaxation=1.0, device=0, rank=0, world_size=1, capacity=None, near_stiffness=None,
-                solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0, **params):
+                solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0, halo_rows=0, halo_capacity=0, **params):
     """c3 / c4: nx x ny block (default square), 4 boundary planes, dam-break under gravity."""
     ny = nx if ny is None else ny
     width, height = _domain(nx, spacing)
     n = nx * ny
     if capacity is None:
-        capacity = n + 1024 if world_size == 1 else int(n / world_size * 1.6) + 65536
+        capacity = n + 1024 if world_size == 1 else min(n + 1024, int(n / world_size * 3.0) + 65536)
     sim = ParticleSimulation(domain_width=width, domain_height=height, cell_size=KERNEL_HEIGHT, max_particles=capacity,
                              device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size,
-                             solver=solver, sweep_capacity=sweep_capacity)
+                             solver=solver, sweep_capacity=sweep_capacity, halo_rows=halo_rows, halo_capacity=halo_capacity)
     p = sim.GetParams()
     p.particle_spacing = spacing
     if near_stiffness is not None:
@@ -47,6 +47,16 @@ def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mo
     cy = -hh + ny * spacing * 0.5 + 0.05
     sim.scene = {"nx": nx, "ny": ny, "spacing": spacing, "center": (cx, cy), "seed": seed, "width": width, "height": height}
     return sim
+
+
+def block_strips(sim, world_size):
+    """Row ranges [(lo, hi)] that split the block's rows evenly (the last strip also owns the empty
+    rows above the block).  Static: SURVEY.md 8(e)'s periodic rebalancing is future work."""
+    sc = sim.scene
+    gx, gy = sim.grid_dims()
+    rows = min(gy, int(np.ceil((sc["ny"] * sc["spacing"] + 0.1) / KERNEL_HEIGHT)) + 1)
+    cuts = [int(round(rows * r / world_size)) for r in range(world_size)] + [gy]
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
 def fill_block(sim):

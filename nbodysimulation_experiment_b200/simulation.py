@@ -28,7 +28,7 @@ class ParticleSimulation:
 
     def __init__(self, domain_width=None, domain_height=None, cell_size=None, max_particles=None, device=0,
                  fp_mode=_lib.SPH_FP_EXACT, flags=0, relaxation=1.0, rank=0, world_size=1, halo_capacity=0,
-                 solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0):
+                 solver=_lib.SPH_SOLVER_COLORED_GS, sweep_capacity=0, halo_rows=0):
         self._lib = _lib.load()
         cfg = SphConfig()
         self._check(self._lib.sph_config_default(C.byref(cfg)), None)
@@ -49,6 +49,7 @@ class ParticleSimulation:
         cfg.rank = rank
         cfg.world_size = world_size
         cfg.halo_capacity = halo_capacity
+        cfg.halo_rows = halo_rows
         self.config = cfg
         self._h = _lib.c_vp()
         self._check(self._lib.sph_create(C.byref(cfg), C.byref(self._h)), None)
@@ -195,6 +196,51 @@ class ParticleSimulation:
 
     def Sync(self):
         self._check(self._lib.sph_sync(self._h))
+
+    # -- multi-GPU plumbing (one process per GPU) ---------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id; create on rank 0 and broadcast (e.g. with torch.distributed)."""
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.load().sph_comm_unique_id(C.cast(buf, _lib.c_vp))
+        if rc != 0:
+            raise SphError(rc, "sph_comm_unique_id failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.sph_comm_init(self._h, C.cast(buf, _lib.c_vp)))
+
+    def set_strip(self, row_begin, row_end):
+        self._check(self._lib.sph_set_strip(self._h, row_begin, row_end))
+
+    def get_strip(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._check(self._lib.sph_get_strip(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def local_particle_count(self):
+        out = C.c_uint64()
+        self._check(self._lib.sph_local_particle_count(self._h, C.byref(out)))
+        return out.value
+
+    def read_owned(self, records=True, render=False, capacity=None):
+        """ids (+ ParticleData records, + positions/colours) of the particles this rank owns."""
+        cap = int(capacity or self.config.max_particles)
+        ids = np.zeros(cap, np.uint32)
+        rec = np.zeros((cap, 12), np.float32) if records else None
+        pos = np.zeros((cap, 2), np.float32) if render else None
+        col = np.zeros((cap, 4), np.float32) if render else None
+        n = C.c_uint64()
+        self._check(self._lib.sph_read_owned(self._h, ids.ctypes.data, rec.ctypes.data if records else None, 48, pos.ctypes.data if render else None, 8,
+                                             col.ctypes.data if render else None, 16, C.byref(n)))
+        k = n.value
+        out = {"ids": ids[:k]}
+        if records:
+            out["records"] = rec[:k]
+        if render:
+            out["positions"], out["colors"] = pos[:k], col[:k]
+        return out
 
     def grid_dims(self):
         gx, gy = C.c_int32(), C.c_int32()

@@ -543,7 +543,7 @@ void oracle_pass_density(SphOracle *o) { run_ranges(o, density_range, 0.0f); }
 void oracle_pass_viscosity(SphOracle *o, float dt) {
 	if (o->mode == ORACLE_MODE_COLORED) {
 		viscosity_colored(o, dt);
-	} else if (o->mode == ORACLE_MODE_JACOBI) {
+	} else if (o->mode == ORACLE_MODE_JACOBI || o->mode == ORACLE_MODE_HYBRID) {
 		ensure_scratch(o);
 		run_ranges(o, viscosity_range_jacobi, dt);
 		for (uint64_t i = 0; i < o->n; ++i) o->p[i].vel = o->scratch[i];
@@ -553,7 +553,7 @@ void oracle_pass_viscosity(SphOracle *o, float dt) {
 }
 
 void oracle_pass_delta(SphOracle *o, float dt) {
-	if (o->mode == ORACLE_MODE_COLORED) {
+	if (o->mode == ORACLE_MODE_COLORED || o->mode == ORACLE_MODE_HYBRID) {
 		delta_colored(o, dt);
 	} else if (o->mode == ORACLE_MODE_JACOBI) {
 		ensure_scratch(o);

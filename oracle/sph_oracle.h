@@ -30,9 +30,10 @@ enum {
 	ORACLE_MODE_JACOBI = 1,   /* the deterministic per-particle gather the GPU implements: every
 	                             pair term evaluated from the pass's input state; candidates walked
 	                             in (dy, dx, ascending particle id) order */
-	ORACLE_MODE_COLORED = 2   /* the reference's in-place half-weight pair updates swept race-free:
+	ORACLE_MODE_COLORED = 2,  /* the reference's in-place half-weight pair updates swept race-free:
 	                             nine cell colours (cx mod 3, cy mod 3), ascending id inside a cell,
 	                             32-lane evaluation of each particle's loop (see sph_oracle.c) */
+	ORACLE_MODE_HYBRID = 3    /* viscosity as in JACOBI (gather), pressure displacement as in COLORED */
 };
 
 enum { ORACLE_BODY_PLANE = 1, ORACLE_BODY_CIRCLE = 2, ORACLE_BODY_SEGMENT = 3, ORACLE_BODY_POLYGON = 4 };

@@ -20,6 +20,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsphref.so")
 MODE_GS_INDEX = 0
 MODE_JACOBI = 1
 MODE_COLORED = 2
+MODE_HYBRID = 3
 
 f32 = C.c_float
 vp = C.c_void_p
