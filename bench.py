@@ -109,36 +109,48 @@ def run_ours(args):
     import torch.distributed as dist
 
     from nbodysimulation_experiment_b200 import (SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER,
-                                                 pinned_empty, scenes)
+                                                 ParticleSimulation, pinned_empty, scenes)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = WORKLOADS[args.workload]
-    nx = args.nx or wl["nx"]
+    # weak scaling: the block grows with the GPU count so that every strip holds ~nx*nx particles
+    nx_one = args.nx or wl["nx"]
+    nx = nx_one if world == 1 else int(round(nx_one * world ** 0.5 / 32.0)) * 32
     spacing = wl["spacing"]
     fp_mode = SPH_FP_FAST if args.fp == "fast" else SPH_FP_EXACT
     gravity = scene_gravity(nx, spacing, wl["gravity_scale"] or args.scaled_gravity)
     solver = SPH_SOLVER_GATHER if args.solver == "gather" else SPH_SOLVER_COLORED_GS
     relaxation = args.relaxation if args.relaxation else wl["relaxation"]
+    uid = [ParticleSimulation.comm_unique_id() if (rank == 0 and world > 1) else None, ParticleSimulation.comm_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
 
-    def make(flags=0):
+    def make(flags=0, which=0):
         sim = scenes.block_scene(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=relaxation, device=local_rank,
-                                 solver=solver, sweep_capacity=args.sweep_capacity)
+                                 solver=solver, sweep_capacity=args.sweep_capacity, rank=rank, world_size=world, halo_rows=args.halo_rows)
+        if world > 1:
+            sim.comm_init(uid[which])
+            sim.set_strip(*scenes.block_strips(sim, world)[rank])
         return scenes.fill_block(sim)
 
-    if world > 1:
-        raise SystemExit("multi-GPU strips are not wired in this build")
+    def all_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sim = make()
-    n = sim.GetParticleCount()
+    n_total = nx * nx
+    n_local = sim.local_particle_count()
     gx, gy = sim.grid_dims()
     cells = gx * gy
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -162,77 +174,80 @@ def run_ours(args):
     ms = sim.elapsed_ms(0, 1)
     barrier()
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    stats = sim.GetStats()
-    value = n * world * args.steps / (ms * 1e-3)
+    ms = all_max(ms)
+    stats = sim.GetStats()  # raises if a capacity flag was set on the device
+    value = n_total * args.steps / (ms * 1e-3)
 
-    # ---- e2e: Update + Render readback (positions + colours, creation order) into pinned host memory,
-    # the per-frame traffic of the reference's app loop (app.cpp:231-233,286-289) -------------------
-    pos_host, own_p = pinned_empty((n, 2), np.float32)
-    col_host, own_c = pinned_empty((n, 4), np.float32)
-    e2e_steps = max(3, min(args.steps, 64))
-    params_blob = np.zeros(16, np.float32)  # per-step host inputs: dt, gravity, external force (bytes counted below)
+    # ---- e2e: Update + Render readback (positions + colours) into host memory every step, the per-frame
+    # traffic of the reference's app loop (app.cpp:231-233,286-289).  One GPU: creation-order arrays in pinned
+    # memory.  Strips: each rank reads back the particles it owns (compacted, with their ids). ----------------
+    e2e_steps = max(3, min(args.steps, 32))
+    params_blob = np.zeros(16, np.float32)  # per-step host inputs: dt, gravity, external force
+    d2h = 0
+    if world == 1:
+        pos_host, own_p = pinned_empty((n_total, 2), np.float32)
+        col_host, own_c = pinned_empty((n_total, 4), np.float32)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         sim.SetGravity(gravity)
         sim.Update(DT)
-        sim.Render(pos_host, col_host)  # D2H inside, synchronises
+        if world == 1:
+            sim.Render(pos_host, col_host)  # D2H inside, synchronises
+            d2h = n_total * 24
+        else:
+            got = sim.read_owned(records=False, render=True)
+            d2h = len(got["ids"]) * 28
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = n * world * e2e_steps / e2e_s
-    assert np.isfinite(pos_host).all()
-    own_p.free()
-    own_c.free()
+    e2e_s = all_max(time.perf_counter() - t0)
+    e2e_value = n_total * e2e_steps / e2e_s
+    if world == 1:
+        assert np.isfinite(pos_host).all()
+        own_p.free()
+        own_c.free()
     sim.close()
 
     # ---- per-phase device times (separate pass: the event brackets serialise host and device) --------
+    psim = make(flags=SPH_FLAG_PHASE_TIMING, which=1)
+    for _ in range(3):
+        psim.Update(DT)
+    psim.ResetStats()
+    for _ in range(max(3, min(args.steps, 20))):
+        psim.Update(DT)
+    phases, _ = psim.phase_ms()
+    n_phase_local = psim.local_particle_count()
+    psim.close()
     roofline = None
-    phases = None
     if rank == 0:
-        psim = make(flags=SPH_FLAG_PHASE_TIMING)
-        for _ in range(3):
-            psim.Update(DT)
-        psim.ResetStats()
-        for _ in range(max(3, min(args.steps, 20))):
-            psim.Update(DT)
-        phases, _ = psim.phase_ms()
-        psim.close()
         peak, peak_src = measured_peak_gbs()
         dom = max((k for k in phases if k != "exchange"), key=lambda k: phases[k])
-        dom_bytes = PHASE_BYTES[dom] * n
+        dom_bytes = PHASE_BYTES[dom] * n_phase_local
         achieved = dom_bytes / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
-        step_bytes = BYTES_PER_PARTICLE_STEP * n + BYTES_PER_CELL_STEP * cells
+        step_bytes = BYTES_PER_PARTICLE_STEP * n_total + BYTES_PER_CELL_STEP * cells
+        step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-            "kernel_ms": phases[dom],
-            "step_model": {"bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
-                           "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "note": "the gather kernels are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/",
+            "bound": "hbm", "kernel": dom + (" (9 colour launches)" if solver == SPH_SOLVER_COLORED_GS and dom in ("viscosity", "delta") else ""),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": phases[dom],
+            "step_model": {"bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
+            "note": "the pair passes are FP32-issue bound, not HBM bound (DESIGN.md, profiles/); rank 0's phases",
         }
 
-    cpu = cpu_baseline(nx, spacing, gravity, relaxation) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    cpu = cpu_baseline(nx_one, spacing, gravity, relaxation) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {nx}x{nx} = {n} particles/GPU, spacing {spacing}, h = cell = 0.3, dt = 1/60, "
+            "config": {"workload": f"{args.workload}: {nx}x{nx} = {n_total} particles on {world} GPU(s), spacing {spacing}, h = cell = 0.3, dt = 1/60, "
                                    f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}",
-                       "particles": n * world, "cells": cells, "candidates_per_particle": stats.pair_candidates / max(n, 1),
+                       "particles": n_total, "particles_rank0": n_local, "cells": cells,
+                       "candidates_per_particle_rank0": stats.pair_candidates / max(n_local, 1),
                        "l2": "state streamed once per phase (>130 MB/step) and a 256 MiB L2 flush before the timed region",
                        "parallelism": f"ystrip{world}"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(n * 24),
-                    "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4) to pinned host memory"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4" + (" + id" if world > 1 else "") + ") to host memory"},
             "gpu_launches": KERNELS_PER_STEP[args.solver] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
@@ -345,6 +360,7 @@ def main():
     ap.add_argument("--solver", default="gs", choices=["gs", "gather"], help="coloured Gauss-Seidel sweeps (default) or Jacobi gather")
     ap.add_argument("--relaxation", type=float, default=0.0, help="gather only: omega")
     ap.add_argument("--sweep-capacity", type=int, default=0)
+    ap.add_argument("--halo-rows", type=int, default=0)
     ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -26,7 +26,9 @@ def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mo
     width, height = _domain(nx, spacing)
     n = nx * ny
     if capacity is None:
-        capacity = n + 1024 if world_size == 1 else min(n + 1024, int(n / world_size * 3.0) + 65536)
+        # a strip holds what it owns (the dam collapses into the lower strips: allow 3x the even share)
+        # plus the ghost copies of both neighbours
+        capacity = n + 1024 if world_size == 1 else min(n, int(n / world_size * 3.0)) + int(n / world_size * 0.75) + 65536
     sim = ParticleSimulation(domain_width=width, domain_height=height, cell_size=KERNEL_HEIGHT, max_particles=capacity,
                              device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size,
                              solver=solver, sweep_capacity=sweep_capacity, halo_rows=halo_rows, halo_capacity=halo_capacity)

@@ -49,10 +49,19 @@ def main():
         print(f"strips {strips} owned {counts} total {sum(counts)} of {n_total}", flush=True)
     assert sum(counts) == n_total, counts
 
-    for _ in range(a.steps):
-        sim.Update(dt)
-    mine = sim.read_owned(records=True)
-    st = sim.GetStats()  # raises on overflow flags
+    err = None
+    try:
+        for _ in range(a.steps):
+            sim.Update(dt)
+        mine = sim.read_owned(records=True)
+        sim.GetStats()  # raises on overflow flags
+    except Exception as e:  # fail fast on every rank instead of hanging the others in a collective
+        err = repr(e)
+    flag = torch.tensor([0 if err is None else 1], device="cuda")
+    dist.all_reduce(flag)
+    if flag.item():
+        print(f"rank {rank}: step loop failed: {err}", flush=True)
+        os._exit(2)
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine["ids"], mine["records"]))
     ok = True
