@@ -513,17 +513,35 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 	return v;
 }
 
-// state = pos (SWEEP_DELTA: read+written) or vel (SWEEP_VISCOSITY: read+written, pos read-only)
+// Per particle i of the cell the candidate loop runs in two stages.  Stage 1 tests every candidate
+// against h (5 flops) and compacts the ones in range into a queue (ballot + popc); stage 2 evaluates
+// only those, with all 32 lanes busy: the h-th candidate in range belongs to lane h mod 32.  About a
+// third of the candidates are in range, so this removes most of the divergence of the expensive
+// part (sqrt, 1/r, the pair term).
+//
+// Shared memory per warp: sPos[cap] (+ sVel[cap] for viscosity) + queue[cap] (uint16).  A block with
+// more than `cap` candidates is not staged: it reads and writes the sorted arrays through L2 and uses
+// the whole per-warp area as its queue, which bounds it at sweep_queue_capacity(cap) candidates
+// (the reference asserts at 1000, demo4.cpp:199).
+__host__ __device__ inline uint32_t sweep_bytes_per_warp(uint32_t cap, int pass) { return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) + cap * 2u; }
+__host__ __device__ inline uint32_t sweep_queue_capacity(uint32_t cap, int pass) { return sweep_bytes_per_warp(cap, pass) / 2u; }
+
 template <class M, int PASS>
 __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
                                                                           const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
-                                                                          float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap) {
-	extern __shared__ float2 sweepSmem[];
-	const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
-	float2 *sPos = sweepSmem + (size_t)w * cap * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+                                                                          float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
+                                                                          Counters *__restrict__ ctr) {
+	extern __shared__ __align__(16) unsigned char sweepSmem[];
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+	unsigned char *mine = sweepSmem + (size_t)w * sweep_bytes_per_warp(cap, PASS);
+	float2 *sPos = reinterpret_cast<float2 *>(mine);
 	float2 *sVel = sPos + cap; // viscosity only
+	uint16_t *queueStaged = reinterpret_cast<uint16_t *>(sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1));
+	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
+	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
 	const uint32_t nList = *colorCount;
 	const int nRows = g.rowHi - g.rowLo;
+	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
 	for (uint32_t idx = blockIdx.x * SPH_SWEEP_WARPS + w; idx < nList; idx += gridDim.x * SPH_SWEEP_WARPS) {
 		const uint32_t c = colorList[idx];
 		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
@@ -546,7 +564,11 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 		// candidate t of the block -> index in the sorted arrays
 		auto gidx = [&](uint32_t t) { return t < off1 ? lo[0] + t : (t < off2 ? lo[1] + (t - off1) : lo[2] + (t - off2)); };
 		const bool staged = T <= cap;
-		float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
+		if (!staged && T > wideCap) { // denser than anything the queue can hold: report, leave the cell alone
+			if (lane == 0) atomicOr(&ctr->overflow, 4u);
+			continue;
+		}
+		uint16_t *queue = staged ? queueStaged : queueWide;
 		if (staged) {
 			for (uint32_t t = lane; t < T; t += 32) {
 				const uint32_t j = gidx(t);
@@ -573,45 +595,47 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 					ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
 					ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
 				}
+				// stage 1: which candidates are within h (sph.h:488,502)
+				uint32_t nHit = 0;
+				for (uint32_t tb = 0; tb < T; tb += 32) {
+					const uint32_t t = tb + lane;
+					bool hit = false;
+					if (t < T) {
+						const float2 xj = staged ? sPos[t] : __ldcg(&pos[gidx(t)]);
+						const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+						hit = M::dot2(rx, rx, ry, ry) < k.h2;
+					}
+					const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+					if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
+					nHit += (uint32_t)__popc(mask);
+				}
+				__syncwarp();
+				// stage 2: the pair terms, partner updated at once (demo4.cpp:233-234, 250-251)
 				float ax = 0.0f, ay = 0.0f;
-				for (uint32_t t = lane; t < T; t += 32) {
+				for (uint32_t q = lane; q < nHit; q += 32) {
+					const uint32_t t = queue[q];
 					bool hit;
-					if (staged) {
-						if (PASS == SWEEP_DELTA) {
-							const float2 xj = sPos[t];
-							const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
-							if (hit) {
-								sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
-								ax = __fsub_rn(ax, hlf.x);
-								ay = __fsub_rn(ay, hlf.y);
-							}
-						} else {
-							const float2 vj = sVel[t];
-							const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, sPos[t], vj, hit);
-							if (hit) {
-								sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
-								ax = __fsub_rn(ax, hlf.x);
-								ay = __fsub_rn(ay, hlf.y);
-							}
-						}
+					if (PASS == SWEEP_DELTA) {
+						float2 *slot = staged ? &sPos[t] : &pos[gidx(t)];
+						const float2 xj = staged ? *slot : __ldcg(slot);
+						const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+						const float2 moved = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+						if (staged) *slot = moved;
+						else __stcg(slot, moved);
+						ax = __fsub_rn(ax, hlf.x);
+						ay = __fsub_rn(ay, hlf.y);
 					} else {
-						const uint32_t j = gidx(t);
-						if (PASS == SWEEP_DELTA) {
-							const float2 xj = __ldcg(&pos[j]);
-							const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
-							if (hit) {
-								__stcg(&pos[j], make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y)));
-								ax = __fsub_rn(ax, hlf.x);
-								ay = __fsub_rn(ay, hlf.y);
-							}
-						} else {
-							const float2 vj = __ldcg(&vel[j]);
-							const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, __ldcg(&pos[j]), vj, hit);
-							if (hit) {
-								__stcg(&vel[j], make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y)));
-								ax = __fsub_rn(ax, hlf.x);
-								ay = __fsub_rn(ay, hlf.y);
-							}
+						const uint32_t j = staged ? 0u : gidx(t);
+						float2 *slot = staged ? &sVel[t] : &vel[j];
+						const float2 vj = staged ? *slot : __ldcg(slot);
+						const float2 xj = staged ? sPos[t] : __ldcg(&pos[j]);
+						const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, xj, vj, hit);
+						if (hit) {
+							const float2 moved = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+							if (staged) *slot = moved;
+							else __stcg(slot, moved);
+							ax = __fsub_rn(ax, hlf.x);
+							ay = __fsub_rn(ay, hlf.y);
 						}
 					}
 				}

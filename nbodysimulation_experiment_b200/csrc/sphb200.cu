@@ -109,6 +109,10 @@ struct SphSim {
 	// occupied cells per colour for the coloured Gauss-Seidel sweeps
 	uint32_t *colorCount = nullptr, *colorList = nullptr;
 	uint32_t listStride = 0, sweepCap = 512;
+	bool sweepAdaptive = true;       // pick the staging capacity from the candidate-list maximum of recent steps
+	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
+	cudaEvent_t lagEvent = nullptr;
+	bool lagPending = false;
 
 	std::vector<DevBody> bodies;
 	DevBody *dBodies = nullptr;
@@ -384,7 +388,7 @@ void launch_density(SphSim *s, const PairParams &k, unsigned nb) {
 // nine launches, one per cell colour; in place on pos (delta) or vel (viscosity)
 template <class M, int PASS>
 void launch_sweeps(SphSim *s, const PairParams &k) {
-	const size_t smem = (size_t)SPH_SWEEP_WARPS * s->sweepCap * sizeof(float2) * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+	const size_t smem = (size_t)SPH_SWEEP_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
 	static bool attrSet = false;
 	if (!attrSet) {
 		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -395,7 +399,7 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 	unsigned blocks = (unsigned)std::min<uint64_t>((cells + SPH_SWEEP_WARPS - 1) / SPH_SWEEP_WARPS, 148u * 64u);
 	for (int color = 0; color < 9; ++color)
 		color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList + (size_t)color * s->listStride,
-		                                                                             s->colorCount + color, s->pos.in(), s->vel.in(), s->press.in(), s->sweepCap);
+		                                                                             s->colorCount + color, s->pos.in(), s->vel.in(), s->press.in(), s->sweepCap, s->dCtr);
 }
 
 int run_viscosity(SphSim *s, const PairParams &k, unsigned nb) {
@@ -540,6 +544,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 		return fail(nullptr, SPH_ERR_INVALID, "unknown solver %d", cfg->solver);
 	}
 	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 512u;
+	s->sweepAdaptive = cfg->sweep_capacity == 0;
 	if (s->sweepCap < 32 || s->sweepCap > 3072) {
 		delete s;
 		return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..3072", s->sweepCap);
@@ -574,6 +579,9 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	CUC(cudaMalloc(&s->dCtr, sizeof(Counters)));
 	CUC(cudaMemset(s->dCtr, 0, sizeof(Counters)));
 	CUC(cudaMallocHost(&s->hCtr, sizeof(Counters)));
+	CUC(cudaMallocHost(&s->hCtrLag, sizeof(Counters)));
+	memset(s->hCtrLag, 0, sizeof(Counters));
+	CUC(cudaEventCreateWithFlags(&s->lagEvent, cudaEventDisableTiming));
 	const size_t cap = s->capacity;
 	CUC(alloc2(s->pos, cap));
 	CUC(alloc2(s->prev, cap));
@@ -658,6 +666,8 @@ int sph_destroy(SphHandle s) {
 	if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
 	cudaFree(s->dCtr);
 	if (s->hCtr) cudaFreeHost(s->hCtr);
+	if (s->hCtrLag) cudaFreeHost(s->hCtrLag);
+	if (s->lagEvent) cudaEventDestroy(s->lagEvent);
 	for (auto &e : s->phaseEv)
 		if (e) cudaEventDestroy(e);
 	for (auto &e : s->marks)
@@ -1028,6 +1038,13 @@ int sph_step(SphHandle s, float dt) {
 	}
 	int rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
+	if (s->sweepAdaptive && s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
+		// shared-memory staging sized to the longest candidate list seen a step or two ago (+25 %);
+		// anything longer still works through the L2 path, so a stale value only costs speed
+		const uint32_t longest = s->hCtrLag->maxNbr;
+		if (longest) s->sweepCap = std::min(1024u, std::max(96u, ((longest + longest / 4 + 31u) / 32u) * 32u));
+		s->lagPending = false;
+	}
 	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
 	const PairParams k = pair_params(s, dt);
 	const unsigned nb = blocks_for(s->hostN);
@@ -1054,6 +1071,11 @@ int sph_step(SphHandle s, float dt) {
 	CU(s, cudaGetLastError());
 	s->steps++;
 	s->steppedOnce = true;
+	if (s->sweepAdaptive && !s->lagPending) {
+		CU(s, cudaMemcpyAsync(s->hCtrLag, s->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, s->stream));
+		CU(s, cudaEventRecord(s->lagEvent, s->stream));
+		s->lagPending = true;
+	}
 
 	if (s->cfg.flags & SPH_FLAG_PHASE_TIMING) {
 		// event k+1 closes phase k; the exchange sits between predict and scan, so its event (index
@@ -1157,7 +1179,9 @@ int sph_get_stats(SphHandle s, SphStats *out) {
 		out->time_delta_positions = (float)(s->phaseMs[PH_DELTA] * inv);
 		out->time_collisions = (float)(s->phaseMs[PH_COLLIDE] * inv);
 	}
-	if (c.overflow) return fail(s, SPH_ERR_CAPACITY, "device reported a capacity overflow (flags %u)", c.overflow);
+	if (c.overflow)
+		return fail(s, SPH_ERR_CAPACITY, "device reported a capacity overflow (flags %u: 1 = particles, 2 = halo buffer, 4 = more candidates in one 3x3 block than the sweep queue holds)",
+		            c.overflow);
 	return SPH_OK;
 }
 

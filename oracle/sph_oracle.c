@@ -450,7 +450,7 @@ static void delta_range_jacobi(SphOracle *o, int64_t s, int64_t e, float dt) {
  * (cx mod 3, cy mod 3) agree have disjoint 3x3 footprints, so sweeping the nine colours one after
  * another, cells of a colour in any order, particles of a cell by ascending id, is a legitimate
  * race-free in-place sweep.  Inside one particle's loop the pair terms are evaluated by 32 "lanes"
- * (candidate k belongs to lane k mod 32) from the particle's state at loop entry; partners are
+ * (the n-th candidate within h belongs to lane n mod 32) from the particle's state at loop entry; partners are
  * updated immediately, the particle's own change is summed per lane, combined by a 5-stage
  * butterfly and applied at the end - exactly what the CUDA kernel does, so results are bit-equal. */
 static float butterfly_sum(float part[32]) {
@@ -475,12 +475,13 @@ static void delta_colored(SphOracle *o, float dt) {
 			memset(px, 0, sizeof(px));
 			memset(py, 0, sizeof(py));
 			uint64_t b0 = nbr_begin(o, i), e0 = nbr_end(o, i);
+			uint32_t inRange = 0; /* the n-th candidate within h is evaluated by lane n mod 32 */
 			for (uint64_t k = b0; k < e0; ++k) {
 				Particle *b = &o->p[o->nbr[k]];
-				int lane = (int)((k - b0) & 31u);
 				V2 rij = v2_sub(b->cur, xi);
 				float r2 = v2_dot(rij, rij);
 				if (r2 < (h * h)) {
+					int lane = (int)(inRange++ & 31u);
 					float r = sqrtf(r2);
 					V2 nrm = v2_normalize(rij);
 					float term = 1.0f - r * invH;
@@ -507,12 +508,13 @@ static void viscosity_colored(SphOracle *o, float dt) {
 			memset(px, 0, sizeof(px));
 			memset(py, 0, sizeof(py));
 			uint64_t b0 = nbr_begin(o, i), e0 = nbr_end(o, i);
+			uint32_t inRange = 0;
 			for (uint64_t k = b0; k < e0; ++k) {
 				Particle *b = &o->p[o->nbr[k]];
-				int lane = (int)((k - b0) & 31u);
 				V2 rij = v2_sub(b->cur, xi);
 				float r2 = v2_dot(rij, rij);
 				if (r2 < (h * h)) {
+					int lane = (int)(inRange++ & 31u);
 					float r = sqrtf(r2);
 					float q = r * invH;
 					V2 nrm = v2_normalize(rij);
