@@ -526,6 +526,116 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 __host__ __device__ inline uint32_t sweep_bytes_per_warp(uint32_t cap, int pass) { return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) + cap * 2u; }
 __host__ __device__ inline uint32_t sweep_queue_capacity(uint32_t cap, int pass) { return sweep_bytes_per_warp(cap, pass) / 2u; }
 
+// One cell, one warp.  STAGED: the block's candidates live in shared memory (sPos/sVel, padded to a
+// multiple of 32 with far-away sentinels so stage 1 needs no bounds test); otherwise they are read
+// and written in the sorted arrays through L2.
+struct SweepBlock {
+	uint32_t lo0, lo1, lo2, off1, off2, T; // three slabs of the sorted arrays and their offsets among the candidates
+	uint32_t ownLo, m, ownOff;             // the cell's own particles: first sorted index, count, first candidate slot
+	__device__ __forceinline__ uint32_t gidx(uint32_t t) const { return t < off1 ? lo0 + t : (t < off2 ? lo1 + (t - off1) : lo2 + (t - off2)); }
+};
+
+template <class M, int PASS, bool STAGED>
+__device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock &b, float2 *pos, float2 *vel, const float2 *__restrict__ press,
+                                           float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask) {
+	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
+	const uint32_t Tpad = (b.T + 31u) & ~31u;
+	if (STAGED) {
+		for (uint32_t t = lane; t < Tpad; t += 32) {
+			if (t < b.T) {
+				const uint32_t j = b.gidx(t);
+				sPos[t] = pos[j];
+				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
+			} else {
+				sPos[t] = make_float2(3.0e18f, 3.0e18f); // never within h of anything
+			}
+		}
+		__syncwarp();
+	}
+	for (uint32_t kBase = 0; kBase < b.m; kBase += 32) {
+		float2 myPress = make_float2(0.0f, 0.0f);
+		if (PASS == SWEEP_DELTA && kBase + lane < b.m) myPress = press[b.ownLo + kBase + lane];
+		const uint32_t kEnd = min(b.m - kBase, 32u);
+		for (uint32_t kk = 0; kk < kEnd; ++kk) {
+			const uint32_t si = b.ownOff + kBase + kk; // this particle's slot among the candidates
+			float2 xi, vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
+			if (STAGED) {
+				xi = sPos[si];
+				if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
+			} else {
+				xi = __ldcg(&pos[b.ownLo + kBase + kk]);
+				if (PASS == SWEEP_VISCOSITY) vi = __ldcg(&vel[b.ownLo + kBase + kk]);
+			}
+			if (PASS == SWEEP_DELTA) {
+				ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
+				ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
+			}
+			// stage 1: which candidates are within h (sph.h:488,502)
+			uint32_t nHit = 0;
+#pragma unroll 2
+			for (uint32_t tb = 0; tb < Tpad; tb += 32) {
+				const uint32_t t = tb + lane;
+				float2 xj;
+				if (STAGED) xj = sPos[t];
+				else xj = (t < b.T) ? __ldcg(&pos[b.gidx(t)]) : make_float2(3.0e18f, 3.0e18f);
+				const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+				const bool hit = M::dot2(rx, rx, ry, ry) < k.h2;
+				const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+				if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
+				nHit += (uint32_t)__popc(mask);
+			}
+			__syncwarp();
+			// stage 2: the pair terms, partner updated at once (demo4.cpp:233-234, 250-251)
+			float ax = 0.0f, ay = 0.0f;
+			for (uint32_t q = lane; q < nHit; q += 32) {
+				const uint32_t t = queue[q];
+				bool hit;
+				if (PASS == SWEEP_DELTA) {
+					float2 *slot = STAGED ? &sPos[t] : &pos[b.gidx(t)];
+					const float2 xj = STAGED ? *slot : __ldcg(slot);
+					const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+					const float2 moved = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+					if (STAGED) *slot = moved;
+					else __stcg(slot, moved);
+					ax = __fsub_rn(ax, hlf.x);
+					ay = __fsub_rn(ay, hlf.y);
+				} else {
+					const uint32_t j = STAGED ? 0u : b.gidx(t);
+					float2 *slot = STAGED ? &sVel[t] : &vel[j];
+					const float2 vj = STAGED ? *slot : __ldcg(slot);
+					const float2 xj = STAGED ? sPos[t] : __ldcg(&pos[j]);
+					const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, xj, vj, hit);
+					if (hit) {
+						const float2 moved = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+						if (STAGED) *slot = moved;
+						else __stcg(slot, moved);
+						ax = __fsub_rn(ax, hlf.x);
+						ay = __fsub_rn(ay, hlf.y);
+					}
+				}
+			}
+			ax = butterfly_sum(ax);
+			ay = butterfly_sum(ay);
+			__syncwarp();
+			if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
+				if (STAGED) {
+					float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
+					*slot = make_float2(__fadd_rn(ax, slot->x), __fadd_rn(ay, slot->y));
+				} else {
+					float2 *slot = &state[b.ownLo + kBase + kk];
+					const float2 cur = __ldcg(slot);
+					__stcg(slot, make_float2(__fadd_rn(ax, cur.x), __fadd_rn(ay, cur.y)));
+				}
+			}
+			__syncwarp();
+		}
+	}
+	if (STAGED) {
+		for (uint32_t t = lane; t < b.T; t += 32) state[b.gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
+		__syncwarp();
+	}
+}
+
 template <class M, int PASS>
 __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
                                                                           const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
@@ -541,7 +651,6 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
 	const uint32_t nList = *colorCount;
 	const int nRows = g.rowHi - g.rowLo;
-	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
 	for (uint32_t idx = blockIdx.x * SPH_SWEEP_WARPS + w; idx < nList; idx += gridDim.x * SPH_SWEEP_WARPS) {
 		const uint32_t c = colorList[idx];
 		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
@@ -558,107 +667,24 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
 			}
 		}
-		const uint32_t ownLo = cellStart[c], m = cellStart[c + 1] - ownLo;
-		const uint32_t off1 = cnt[0], off2 = cnt[0] + cnt[1], T = off2 + cnt[2];
-		const uint32_t ownOff = off1 + (ownLo - lo[1]);
-		// candidate t of the block -> index in the sorted arrays
-		auto gidx = [&](uint32_t t) { return t < off1 ? lo[0] + t : (t < off2 ? lo[1] + (t - off1) : lo[2] + (t - off2)); };
-		const bool staged = T <= cap;
-		if (!staged && T > wideCap) { // denser than anything the queue can hold: report, leave the cell alone
-			if (lane == 0) atomicOr(&ctr->overflow, 4u);
-			continue;
+		SweepBlock b;
+		b.lo0 = lo[0];
+		b.lo1 = lo[1];
+		b.lo2 = lo[2];
+		b.off1 = cnt[0];
+		b.off2 = cnt[0] + cnt[1];
+		b.T = b.off2 + cnt[2];
+		b.ownLo = cellStart[c];
+		b.m = cellStart[c + 1] - b.ownLo;
+		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		if (((b.T + 31u) & ~31u) <= cap) {
+			sweep_cell<M, PASS, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask);
+		} else if (b.T <= wideCap) {
+			sweep_cell<M, PASS, false>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask);
+			__syncwarp();
+		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
+			atomicOr(&ctr->overflow, 4u);
 		}
-		uint16_t *queue = staged ? queueStaged : queueWide;
-		if (staged) {
-			for (uint32_t t = lane; t < T; t += 32) {
-				const uint32_t j = gidx(t);
-				sPos[t] = pos[j];
-				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
-			}
-		}
-		__syncwarp();
-		for (uint32_t kBase = 0; kBase < m; kBase += 32) {
-			float2 myPress = make_float2(0.0f, 0.0f);
-			if (PASS == SWEEP_DELTA && kBase + lane < m) myPress = press[ownLo + kBase + lane];
-			const uint32_t kEnd = min(m - kBase, 32u);
-			for (uint32_t kk = 0; kk < kEnd; ++kk) {
-				const uint32_t si = ownOff + kBase + kk; // this particle's slot among the candidates
-				float2 xi, vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
-				if (staged) {
-					xi = sPos[si];
-					if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
-				} else {
-					xi = __ldcg(&pos[ownLo + kBase + kk]);
-					if (PASS == SWEEP_VISCOSITY) vi = __ldcg(&vel[ownLo + kBase + kk]);
-				}
-				if (PASS == SWEEP_DELTA) {
-					ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
-					ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
-				}
-				// stage 1: which candidates are within h (sph.h:488,502)
-				uint32_t nHit = 0;
-				for (uint32_t tb = 0; tb < T; tb += 32) {
-					const uint32_t t = tb + lane;
-					bool hit = false;
-					if (t < T) {
-						const float2 xj = staged ? sPos[t] : __ldcg(&pos[gidx(t)]);
-						const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-						hit = M::dot2(rx, rx, ry, ry) < k.h2;
-					}
-					const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-					if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
-					nHit += (uint32_t)__popc(mask);
-				}
-				__syncwarp();
-				// stage 2: the pair terms, partner updated at once (demo4.cpp:233-234, 250-251)
-				float ax = 0.0f, ay = 0.0f;
-				for (uint32_t q = lane; q < nHit; q += 32) {
-					const uint32_t t = queue[q];
-					bool hit;
-					if (PASS == SWEEP_DELTA) {
-						float2 *slot = staged ? &sPos[t] : &pos[gidx(t)];
-						const float2 xj = staged ? *slot : __ldcg(slot);
-						const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
-						const float2 moved = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
-						if (staged) *slot = moved;
-						else __stcg(slot, moved);
-						ax = __fsub_rn(ax, hlf.x);
-						ay = __fsub_rn(ay, hlf.y);
-					} else {
-						const uint32_t j = staged ? 0u : gidx(t);
-						float2 *slot = staged ? &sVel[t] : &vel[j];
-						const float2 vj = staged ? *slot : __ldcg(slot);
-						const float2 xj = staged ? sPos[t] : __ldcg(&pos[j]);
-						const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, xj, vj, hit);
-						if (hit) {
-							const float2 moved = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
-							if (staged) *slot = moved;
-							else __stcg(slot, moved);
-							ax = __fsub_rn(ax, hlf.x);
-							ay = __fsub_rn(ay, hlf.y);
-						}
-					}
-				}
-				ax = butterfly_sum(ax);
-				ay = butterfly_sum(ay);
-				__syncwarp();
-				if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
-					if (staged) {
-						float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
-						*slot = make_float2(__fadd_rn(ax, slot->x), __fadd_rn(ay, slot->y));
-					} else {
-						float2 *slot = &state[ownLo + kBase + kk];
-						const float2 cur = __ldcg(slot);
-						__stcg(slot, make_float2(__fadd_rn(ax, cur.x), __fadd_rn(ay, cur.y)));
-					}
-				}
-				__syncwarp();
-			}
-		}
-		if (staged) {
-			for (uint32_t t = lane; t < T; t += 32) state[gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
-		}
-		__syncwarp();
 	}
 }
 
