@@ -172,9 +172,13 @@ int sph_get_stats(SphHandle h, SphStats *out); /* GetStats */
 int sph_read_particles(SphHandle h, void *dst, size_t stride);
 int sph_write_particles(SphHandle h, const void *src, size_t stride); /* inject cur/prev/acc/vel (+ rho,P fields) and re-file the grid */
 /* Render()'s particle section, demo4.cpp:520-531: positions at pos_stride (>= 8) and the colours of
- * SPHGetParticleColor (sph.h:683-695) at color_stride (>= 16), both in creation order.  Buffers may
- * be pageable or pinned; pinned (sph_host_alloc) makes the copy asynchronous until sph_sync. */
+ * SPHGetParticleColor (sph.h:683-695) at color_stride (>= 16), both in creation order.  The state is
+ * snapshotted on the device and copied on a second stream: with pinned buffers (sph_host_alloc) the
+ * call returns at once and the copy overlaps the next sph_step; the data is valid after
+ * sph_wait_render (or sph_sync).  The reference's contract - pointers valid until the frame is
+ * drawn (render.h:342-353) - is met by calling sph_wait_render before drawing. */
 int sph_render_particles(SphHandle h, void *positions, size_t pos_stride, void *colors, size_t color_stride);
+int sph_wait_render(SphHandle h);
 int sph_read_cell_counts(SphHandle h, uint32_t *out);        /* Cell::count per cell, row-major (demo4.h:118-121) */
 int sph_read_cell_of_particle(SphHandle h, int32_t *out_xy); /* ParticleIndex::cellIndex, creation order (demo4.h:112) */
 /* the grid as the GPU holds it: particle ids in cell-sorted order (n entries) and the exclusive

@@ -102,6 +102,7 @@ SIGNATURES = {
     "sph_read_particles": (C.c_int, [c_vp, c_vp, c_sz]),
     "sph_write_particles": (C.c_int, [c_vp, c_vp, c_sz]),
     "sph_render_particles": (C.c_int, [c_vp, c_vp, c_sz, c_vp, c_sz]),
+    "sph_wait_render": (C.c_int, [c_vp]),
     "sph_read_cell_counts": (C.c_int, [c_vp, c_vp]),
     "sph_read_cell_of_particle": (C.c_int, [c_vp, c_vp]),
     "sph_read_sorted_ids": (C.c_int, [c_vp, c_vp]),

@@ -98,6 +98,9 @@ struct SphSim {
 	uint32_t capacity = 0;
 
 	cudaStream_t stream = nullptr;
+	cudaStream_t copyStream = nullptr;          // Render readback overlaps the next Update
+	cudaEvent_t renderReady = nullptr, copyDone = nullptr;
+	bool copyPending = false;
 	Counters *dCtr = nullptr;
 	Counters *hCtr = nullptr; // pinned mirror
 
@@ -171,6 +174,14 @@ int fail(SphSim *s, int code, const char *fmt, ...) {
 	do {                                                  \
 		if (!(h)) return fail(nullptr, SPH_ERR_INVALID, "null handle"); \
 	} while (0)
+
+// strided host<->device copy; the contiguous case must not go through cudaMemcpy2D (a million 8-byte
+// rows copy an order of magnitude slower than one flat transfer)
+inline cudaError_t copy_strided(void *dst, size_t dstPitch, const void *src, size_t srcPitch, size_t width, size_t rows, cudaMemcpyKind kind,
+                                cudaStream_t stream) {
+	if (dstPitch == width && srcPitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, stream);
+	return cudaMemcpy2DAsync(dst, dstPitch, src, srcPitch, width, rows, kind, stream);
+}
 
 inline unsigned blocks_for(uint64_t n) {
 	uint64_t b = (n + SPH_THREADS - 1) / SPH_THREADS;
@@ -576,6 +587,9 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 
 	CUC(cudaSetDevice(cfg->device));
 	CUC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CUC(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+	CUC(cudaEventCreateWithFlags(&s->renderReady, cudaEventDisableTiming));
+	CUC(cudaEventCreateWithFlags(&s->copyDone, cudaEventDisableTiming));
 	CUC(cudaMalloc(&s->dCtr, sizeof(Counters)));
 	CUC(cudaMemset(s->dCtr, 0, sizeof(Counters)));
 	CUC(cudaMallocHost(&s->hCtr, sizeof(Counters)));
@@ -636,6 +650,12 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 int sph_destroy(SphHandle s) {
 	if (!s) return SPH_OK;
 	if (s->stream) cudaStreamSynchronize(s->stream);
+	if (s->copyStream) {
+		cudaStreamSynchronize(s->copyStream);
+		cudaStreamDestroy(s->copyStream);
+	}
+	if (s->renderReady) cudaEventDestroy(s->renderReady);
+	if (s->copyDone) cudaEventDestroy(s->copyDone);
 	free2(s->pos);
 	free2(s->prev);
 	free2(s->vel);
@@ -1095,6 +1115,8 @@ int sph_step(SphHandle s, float dt) {
 int sph_sync(SphHandle s) {
 	CHECK_HANDLE(s);
 	CU(s, cudaStreamSynchronize(s->stream));
+	CU(s, cudaStreamSynchronize(s->copyStream));
+	s->copyPending = false;
 	return SPH_OK;
 }
 
@@ -1202,7 +1224,7 @@ int sph_read_particles(SphHandle s, void *dst, size_t stride) {
 	gather_records_kernel<<<blocks_for(s->hostN), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->id.in(), s->pos.in(), s->prev.in(), s->vel.in(), s->acc.in(),
 	                                                                         s->dens.in(), s->press.in(), s->dRecords, 0u, count);
 	CU(s, cudaGetLastError());
-	CU(s, cudaMemcpy2DAsync(dst, stride, s->dRecords, sizeof(ParticleRecord), sizeof(ParticleRecord), count, cudaMemcpyDeviceToHost, s->stream));
+	CU(s, copy_strided(dst, stride, s->dRecords, sizeof(ParticleRecord), sizeof(ParticleRecord), count, cudaMemcpyDeviceToHost, s->stream));
 	CU(s, cudaStreamSynchronize(s->stream));
 	return SPH_OK;
 }
@@ -1214,7 +1236,7 @@ int sph_write_particles(SphHandle s, const void *src, size_t stride) {
 	if (s->hostN == 0) return SPH_OK;
 	if (!s->dRecords) CU(s, cudaMalloc(&s->dRecords, (size_t)s->capacity * sizeof(ParticleRecord)));
 	const uint32_t n = (uint32_t)s->hostN;
-	CU(s, cudaMemcpy2DAsync(s->dRecords, sizeof(ParticleRecord), src, stride, sizeof(ParticleRecord), n, cudaMemcpyHostToDevice, s->stream));
+	CU(s, copy_strided(s->dRecords, sizeof(ParticleRecord), src, stride, sizeof(ParticleRecord), n, cudaMemcpyHostToDevice, s->stream));
 	scatter_records_kernel<<<blocks_for(n), SPH_THREADS, 0, s->stream>>>(n, s->dRecords, s->id.in(), s->pos.in(), s->prev.in(), s->vel.in(), s->acc.in(),
 	                                                                    s->dens.in(), s->press.in());
 	set_counts_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, n, 0);
@@ -1236,11 +1258,24 @@ int sph_render_particles(SphHandle s, void *positions, size_t posStride, void *c
 		CU(s, cudaMalloc(&s->dRenderCol, (size_t)s->capacity * sizeof(float4)));
 	}
 	const uint32_t count = (uint32_t)std::min<uint64_t>(s->nextId, s->capacity);
+	// the device-side snapshot may only be overwritten once the previous frame's copy has left it
+	if (s->copyPending) CU(s, cudaStreamWaitEvent(s->stream, s->copyDone, 0));
 	render_kernel<<<blocks_for(s->hostN), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->id.in(), s->pos.in(), s->vel.in(), s->dens.in(), s->press.in(),
 	                                                                 s->params.rest_density, s->dRenderPos, s->dRenderCol, 0u, count);
 	CU(s, cudaGetLastError());
-	if (positions) CU(s, cudaMemcpy2DAsync(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), count, cudaMemcpyDeviceToHost, s->stream));
-	if (colors) CU(s, cudaMemcpy2DAsync(colors, colorStride, s->dRenderCol, sizeof(float4), sizeof(float4), count, cudaMemcpyDeviceToHost, s->stream));
+	// the copies run on their own stream, so the next sph_step overlaps them; sph_sync waits for both
+	CU(s, cudaEventRecord(s->renderReady, s->stream));
+	CU(s, cudaStreamWaitEvent(s->copyStream, s->renderReady, 0));
+	if (positions) CU(s, copy_strided(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), count, cudaMemcpyDeviceToHost, s->copyStream));
+	if (colors) CU(s, copy_strided(colors, colorStride, s->dRenderCol, sizeof(float4), sizeof(float4), count, cudaMemcpyDeviceToHost, s->copyStream));
+	CU(s, cudaEventRecord(s->copyDone, s->copyStream));
+	s->copyPending = true;
+	return SPH_OK;
+}
+
+int sph_wait_render(SphHandle s) {
+	CHECK_HANDLE(s);
+	if (s->copyPending) CU(s, cudaEventSynchronize(s->copyDone));
 	return SPH_OK;
 }
 
@@ -1369,9 +1404,9 @@ int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, 
 	if (count) *count = n;
 	if (n == 0) return SPH_OK;
 	if (ids) CU(s, cudaMemcpyAsync(ids, s->dOwnedIds, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-	if (records) CU(s, cudaMemcpy2DAsync(records, recStride, s->dRecords, sizeof(ParticleRecord), sizeof(ParticleRecord), n, cudaMemcpyDeviceToHost, s->stream));
-	if (positions) CU(s, cudaMemcpy2DAsync(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost, s->stream));
-	if (colors) CU(s, cudaMemcpy2DAsync(colors, colStride, s->dRenderCol, sizeof(float4), sizeof(float4), n, cudaMemcpyDeviceToHost, s->stream));
+	if (records) CU(s, copy_strided(records, recStride, s->dRecords, sizeof(ParticleRecord), sizeof(ParticleRecord), n, cudaMemcpyDeviceToHost, s->stream));
+	if (positions) CU(s, copy_strided(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost, s->stream));
+	if (colors) CU(s, copy_strided(colors, colStride, s->dRenderCol, sizeof(float4), sizeof(float4), n, cudaMemcpyDeviceToHost, s->stream));
 	CU(s, cudaStreamSynchronize(s->stream));
 	return SPH_OK;
 }

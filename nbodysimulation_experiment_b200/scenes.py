@@ -7,7 +7,7 @@ counter-hash jitter generated on the device), so nothing is built on the host.
 """
 import numpy as np
 
-from . import _lib
+from . import _lib, strips
 from .simulation import ParticleSimulation
 
 KERNEL_HEIGHT = float(np.float32(6.0) * np.float32(0.05))  # sph.h:35-36
@@ -57,8 +57,7 @@ def block_strips(sim, world_size):
     sc = sim.scene
     gx, gy = sim.grid_dims()
     rows = min(gy, int(np.ceil((sc["ny"] * sc["spacing"] + 0.1) / KERNEL_HEIGHT)) + 1)
-    cuts = [int(round(rows * r / world_size)) for r in range(world_size)] + [gy]
-    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+    return strips.split_rows(rows, gy, world_size)
 
 
 def fill_block(sim):

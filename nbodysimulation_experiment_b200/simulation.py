@@ -128,16 +128,22 @@ class ParticleSimulation:
     def Update(self, deltaTime):
         self._check(self._lib.sph_step(self._h, deltaTime))
 
-    def Render(self, positions=None, colors=None):
-        """The particle section of Render() (demo4.cpp:520-531): positions + colours, creation order."""
+    def Render(self, positions=None, colors=None, wait=True):
+        """The particle section of Render() (demo4.cpp:520-531): positions + colours, creation order.
+        wait=False returns once the copy is enqueued (pinned buffers): it overlaps the next Update and
+        is complete after WaitRender()."""
         n = self.GetParticleCount()
         if positions is None:
             positions = np.empty((n, 2), np.float32)
         if colors is None:
             colors = np.empty((n, 4), np.float32)
         self._check(self._lib.sph_render_particles(self._h, positions.ctypes.data, positions.strides[0], colors.ctypes.data, colors.strides[0]))
-        self.Sync()
+        if wait:
+            self.WaitRender()
         return positions, colors
+
+    def WaitRender(self):
+        self._check(self._lib.sph_wait_render(self._h))
 
     def AddExternalForces(self, force):
         self._check(self._lib.sph_add_external_force(self._h, force[0], force[1]))
