@@ -34,7 +34,11 @@ UNIT = "particle-steps/s"
 
 # BASELINE.json configs[2] / SURVEY.md 8(d) c3.  nx*nx particles per GPU.
 WORKLOADS = {
-    "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=False, relaxation=1.0),
+    # gravity_scale: (0,-10) scaled to the reference scene's hydrostatic head (DESIGN.md "scene scaling"):
+    # at the reference's g a 102-unit column hits the floor at ~45 units/s = 2.5 cells per step and the
+    # fixed-dt relaxation (the reference's as much as ours) produces NaNs by step ~250
+    "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=True, relaxation=1.0),
+    "dambreak_1m_dense": dict(nx=1024, spacing=0.05, gravity_scale=True, relaxation=1.0),
 }
 BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
@@ -355,8 +359,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=256)   # 32 warm-up + 256 timed steps
+    ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dambreak_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=0, help="override the block edge (particles = nx*nx per GPU)")

@@ -75,3 +75,33 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "sph_oracle" not in text and "libsphref" not in text and "oracle_lib" not in text, f
+
+
+def _build_demo(tmp_path):
+    from nbodysimulation_experiment_b200 import build
+
+    lib = build.build()
+    exe = str(tmp_path / "demo_host")
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "demo_host.cpp"), "-L", os.path.dirname(lib),
+                    "-lsphb200", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_host_class_builds_and_refuses_without_gpu(tmp_path):
+    """include/sphb200_sim.hpp (the BaseSimulation-shaped C++ host class) compiles against the C ABI
+    alone; without a device the program fails loudly instead of falling back."""
+    import torch
+
+    exe = _build_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu-marked test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 3 and "no CPU fallback" in out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_class_runs_the_app_loop(tmp_path):
+    exe = _build_demo(tmp_path)
+    out = subprocess.run([exe, "0", "16"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "5300 particles" in out.stdout
