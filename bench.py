@@ -128,6 +128,8 @@ def run_ours(args):
     # weak scaling: the block grows with the GPU count so that every strip holds ~nx*nx particles
     nx_one = args.nx or wl["nx"]
     nx = nx_one if world == 1 else int(round(nx_one * world ** 0.5 / 32.0)) * 32
+    if args.nx_total:  # e.g. 4096 on 8 GPUs = BASELINE.json configs[3], the 16M-particle block
+        nx = args.nx_total
     spacing = wl["spacing"]
     fp_mode = SPH_FP_FAST if args.fp == "fast" else SPH_FP_EXACT
     gravity = scene_gravity(nx, spacing, wl["gravity_scale"] or args.scaled_gravity)
@@ -370,6 +372,7 @@ def main():
     ap.add_argument("--relaxation", type=float, default=0.0, help="gather only: omega")
     ap.add_argument("--sweep-capacity", type=int, default=0)
     ap.add_argument("--halo-rows", type=int, default=0)
+    ap.add_argument("--nx-total", type=int, default=0, help="edge of the whole block, overriding the weak-scaling rule")
     ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")
     args = ap.parse_args()
     if args.impl == "reference":
