@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(SPH_THREADS) unpack_kernel(GridDesc g, Counter
                                                             float2 *__restrict__ pos, float2 *__restrict__ prev, uint32_t *__restrict__ id,
                                                             uint32_t *__restrict__ cellNew, uint32_t *__restrict__ rank, uint32_t *__restrict__ cellCount) {
 	// records land at [n + (count of the buffer unpacked before this one), ...)
+	if (blockIdx.x == 0 && threadIdx.x == 0 && in->count > haloCap) atomicOr(&ctr->overflow, 2u); // the sender packed more than a message ships
 	const uint32_t count = min(in->count, haloCap);
 	const uint32_t first = ctr->n + baseOffset + (before ? min(before->count, haloCap) : 0u);
 	SPH_WARP_LOOP(k, count) {

@@ -52,6 +52,7 @@ struct NcclApi {
 	int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
 	std::string error;
 	bool load() {
 		if (lib) return true;
@@ -77,12 +78,16 @@ struct NcclApi {
 		BIND(Recv, "ncclRecv")
 		BIND(GroupStart, "ncclGroupStart")
 		BIND(GroupEnd, "ncclGroupEnd")
+		BIND(AllReduce, "ncclAllReduce")
 #undef BIND
 		return true;
 	}
 };
 NcclApi g_nccl;
-constexpr int kNcclUint8 = 1; // ncclUint8, nccl.h:279
+constexpr int kNcclUint8 = 1;  // ncclUint8, nccl.h:279
+constexpr int kNcclUint32 = 3; // ncclUint32, nccl.h:281
+constexpr int kNcclMax = 2;    // ncclMax, nccl.h:262
+constexpr int kHaloResizeEvery = 16; // steps between re-sizings of the exchange messages
 
 enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DENSITY, PH_DELTA, PH_COLLIDE, PH_EXCHANGE, PH_COUNT };
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
@@ -131,7 +136,10 @@ struct SphSim {
 	// y-strip decomposition
 	StripDesc strip = {};
 	HaloBuffer *sendBuf[2] = { nullptr, nullptr }, *recvBuf[2] = { nullptr, nullptr }; // [0] = lower neighbour, [1] = upper
-	size_t haloBytes = 0;
+	size_t haloBytes = 0;        // allocation per buffer
+	uint32_t haloMsgRecords = 0; // records actually shipped per message (all ranks agree; re-sized every kHaloResizeEvery steps)
+	uint32_t *dPeak = nullptr;   // [0] peak records packed since the last re-size, [1] all-reduced maximum
+	uint64_t exchanges = 0;
 	NcclComm comm = nullptr;
 	uint32_t *dOwnedCount = nullptr, *dOwnedIds = nullptr;
 
@@ -261,6 +269,12 @@ __global__ void set_counts_kernel(Counters *ctr, uint32_t n, uint32_t nSorted) {
 	ctr->nIn = n;
 	ctr->nOut = nSorted;
 }
+// records packed this step vs the records a message ships: remember the peak, flag what does not fit
+__global__ void note_peak_kernel(const HaloBuffer *down, const HaloBuffer *up, uint32_t *peak, uint32_t msgRecords, Counters *ctr) {
+	const uint32_t most = max(down ? down->count : 0u, up ? up->count : 0u);
+	if (most > peak[0]) peak[0] = most;
+	if (most > msgRecords) atomicOr(&ctr->overflow, 2u);
+}
 __global__ void grow_count_kernel(Counters *ctr, uint32_t n) {
 	ctr->n = n;
 	ctr->nIn = n;
@@ -323,25 +337,43 @@ int exchange_halos(SphSim *s) {
 	const StripDesc &sd = s->strip;
 	if (!s->comm) return fail(s, SPH_ERR_STATE, "sph_comm_init was not called on this multi-GPU handle");
 	NcclApi &nc = g_nccl;
+	// Message size: NCCL needs it on the host, the record counts only exist on the device.  All ranks
+	// therefore ship the same fixed number of records per message, re-agreed every kHaloResizeEvery
+	// steps as 1.5 x the largest count any rank packed since (one stream sync + a 4-byte all-reduce).
+	// The first messages carry the whole buffer.  A count above the agreed size raises the overflow
+	// flag on the sender (pack) and on the receiver (header count > records shipped).
+	if (s->exchanges > 0 && s->exchanges % kHaloResizeEvery == 0) {
+		int rca = nc.AllReduce(s->dPeak, s->dPeak + 1, 1, kNcclUint32, kNcclMax, s->comm, s->stream);
+		if (rca != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce failed: %s", nc.GetErrorString(rca));
+		uint32_t peak = 0;
+		CU(s, cudaMemcpyAsync(&peak, s->dPeak + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+		CU(s, cudaMemsetAsync(s->dPeak, 0, sizeof(uint32_t), s->stream));
+		CU(s, cudaStreamSynchronize(s->stream));
+		const uint64_t want = (uint64_t)peak + peak / 2 + 4096;
+		s->haloMsgRecords = (uint32_t)std::min<uint64_t>(sd.haloCap, want);
+	}
+	s->exchanges++;
+	const size_t msgBytes = sizeof(HaloBuffer) + (size_t)s->haloMsgRecords * sizeof(HaloRecord);
+	note_peak_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1], s->dPeak, s->haloMsgRecords, s->dCtr);
 	int rc = nc.GroupStart();
 	if (rc == 0 && sd.rank > 0) {
-		rc = nc.Send(s->sendBuf[0], s->haloBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
-		if (rc == 0) rc = nc.Recv(s->recvBuf[0], s->haloBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+		rc = nc.Send(s->sendBuf[0], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->recvBuf[0], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
 	}
 	if (rc == 0 && sd.rank + 1 < sd.world) {
-		rc = nc.Send(s->sendBuf[1], s->haloBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
-		if (rc == 0) rc = nc.Recv(s->recvBuf[1], s->haloBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+		rc = nc.Send(s->sendBuf[1], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->recvBuf[1], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
 	}
 	const int rcEnd = nc.GroupEnd();
 	if (rc == 0) rc = rcEnd;
 	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL exchange failed: %s", nc.GetErrorString(rc));
-	const unsigned nb = blocks_for(sd.haloCap);
+	const unsigned nb = blocks_for(s->haloMsgRecords);
 	const GridDesc &g = s->grid;
 	if (sd.rank > 0)
-		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[0], sd.haloCap, s->capacity, 0u, nullptr, s->pos.in(), s->prev.in(), s->id.in(),
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[0], s->haloMsgRecords, s->capacity, 0u, nullptr, s->pos.in(), s->prev.in(), s->id.in(),
 		                                                s->cellNew, s->rank, s->cellCount);
 	if (sd.rank + 1 < sd.world)
-		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[1], sd.haloCap, s->capacity, 0u, sd.rank > 0 ? s->recvBuf[0] : nullptr, s->pos.in(),
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[1], s->haloMsgRecords, s->capacity, 0u, sd.rank > 0 ? s->recvBuf[0] : nullptr, s->pos.in(),
 		                                                s->prev.in(), s->id.in(), s->cellNew, s->rank, s->cellCount);
 	CU(s, cudaGetLastError());
 	return SPH_OK;
@@ -634,6 +666,9 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 		}
 		s->strip.sendDown = s->sendBuf[0];
 		s->strip.sendUp = s->sendBuf[1];
+		s->haloMsgRecords = s->strip.haloCap;
+		CUC(cudaMalloc(&s->dPeak, 2 * sizeof(uint32_t)));
+		CUC(cudaMemset(s->dPeak, 0, 2 * sizeof(uint32_t)));
 		s->hostN = cap; // launch bound: the live count is only known on the device
 	}
 	CUC(cudaMalloc(&s->dOwnedCount, sizeof(uint32_t)));
@@ -681,6 +716,7 @@ int sph_destroy(SphHandle s) {
 		cudaFree(s->sendBuf[d]);
 		cudaFree(s->recvBuf[d]);
 	}
+	cudaFree(s->dPeak);
 	cudaFree(s->dOwnedCount);
 	cudaFree(s->dOwnedIds);
 	if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);

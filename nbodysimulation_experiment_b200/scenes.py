@@ -29,6 +29,11 @@ def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mo
         # a strip holds what it owns (the dam collapses into the lower strips: allow 3x the even share)
         # plus the ghost copies of both neighbours
         capacity = n + 1024 if world_size == 1 else min(n, int(n / world_size * 3.0)) + int(n / world_size * 0.75) + 65536
+    if world_size > 1 and not halo_capacity:
+        # records per exchange message buffer: the block's rows that fit the halo, x6 for the compression
+        # of a collapsing column (the messages themselves shrink to 1.5 x the observed peak after 16 steps)
+        rows_per_rank = max(ny * spacing / KERNEL_HEIGHT / world_size, 1.0)
+        halo_capacity = strips.halo_capacity_estimate(n / world_size, rows_per_rank, halo_rows or strips.DEFAULT_HALO_ROWS, safety=6.0)
     sim = ParticleSimulation(domain_width=width, domain_height=height, cell_size=KERNEL_HEIGHT, max_particles=capacity,
                              device=device, fp_mode=fp_mode, flags=flags, relaxation=relaxation, rank=rank, world_size=world_size,
                              solver=solver, sweep_capacity=sweep_capacity, halo_rows=halo_rows, halo_capacity=halo_capacity)
