@@ -192,6 +192,8 @@ def run_ours(args):
     d2h = 0
     if world == 1:
         frames = [(pinned_empty((n_total, 2), np.float32), pinned_empty((n_total, 4), np.float32)) for _ in range(2)]
+    else:
+        owned_bufs = sim.owned_buffers(records=False, render=True, pinned=True)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -203,7 +205,7 @@ def run_ours(args):
             sim.Render(pos_host, col_host, wait=False)  # snapshot + D2H on the copy stream
             d2h = n_total * 24
         else:
-            got = sim.read_owned(records=False, render=True)
+            got = sim.read_owned(records=False, render=True, buffers=owned_bufs)
             d2h = len(got["ids"]) * 28
     if world == 1:
         sim.WaitRender()

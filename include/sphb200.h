@@ -57,7 +57,8 @@ enum { SPH_FP_EXACT = 0, SPH_FP_FAST = 1 };
 enum { SPH_SOLVER_COLORED_GS = 0, SPH_SOLVER_GATHER = 1 };
 
 enum {
-	SPH_FLAG_PHASE_TIMING = 1u << 0 /* bracket every phase with CUDA events and fill SphStats.time_* (sph.h:131-141) */
+	SPH_FLAG_PHASE_TIMING = 1u << 0, /* bracket every phase with CUDA events and fill SphStats.time_* (sph.h:131-141) */
+	SPH_FLAG_NO_GRAPHS = 1u << 1     /* launch every kernel of a step individually instead of replaying a CUDA graph */
 };
 
 /* Runtime replacement for the compile-time world of sph.h:18-72. */

@@ -92,6 +92,17 @@ constexpr int kHaloResizeEvery = 16; // steps between re-sizings of the exchange
 enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DENSITY, PH_DELTA, PH_COLLIDE, PH_EXCHANGE, PH_COUNT };
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
+struct StepGraphKey {
+	uint32_t parity, sweepCap, nb, nbodies;
+	float2 force;
+	PairParams k;
+};
+struct StepGraph {
+	StepGraphKey key;
+	uint32_t parityAfter = 0;
+	cudaGraphExec_t exec = nullptr;
+};
+
 } // namespace
 
 struct SphSim {
@@ -155,6 +166,10 @@ struct SphSim {
 	uint64_t phaseSteps = 0;
 	float hostEmitterMs = 0.0f;
 	cudaEvent_t marks[8] = {};
+
+	// step graphs
+	bool useGraphs = true;
+	std::vector<StepGraph> graphs;
 
 	std::string err;
 };
@@ -588,6 +603,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	}
 	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 512u;
 	s->sweepAdaptive = cfg->sweep_capacity == 0;
+	s->useGraphs = !(cfg->flags & SPH_FLAG_NO_GRAPHS);
 	if (s->sweepCap < 32 || s->sweepCap > 3072) {
 		delete s;
 		return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..3072", s->sweepCap);
@@ -722,6 +738,8 @@ int sph_destroy(SphHandle s) {
 	if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
 	cudaFree(s->dCtr);
 	if (s->hCtr) cudaFreeHost(s->hCtr);
+	for (StepGraph &g : s->graphs)
+		if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (s->hCtrLag) cudaFreeHost(s->hCtrLag);
 	if (s->lagEvent) cudaEventDestroy(s->lagEvent);
 	for (auto &e : s->phaseEv)
@@ -1082,6 +1100,44 @@ extern "C" int sph_load_scenario(SphHandle s, int idx, int seed) {
 	return SPH_OK;
 }
 
+// one Update() as a sequence of launches on s->stream (also what a step graph captures)
+static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, float2 force, float invDt) {
+	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
+	record_phase(s, 0);
+	begin_step_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
+	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
+	s->accFrom = 0xFFFFFFFFu;
+	record_phase(s, PH_INTEGRATE + 1);
+	run_viscosity(s, k, nb);
+	record_phase(s, PH_VISCOSITY + 1);
+	int rc = launch_grid_build(s, dt, true, false, true);
+	if (rc != SPH_OK) return rc;
+	if (exact) launch_density<Exact>(s, k, nb);
+	else launch_density<Fast>(s, k, nb);
+	record_phase(s, PH_DENSITY + 1);
+	run_delta(s, k, nb);
+	record_phase(s, PH_DELTA + 1);
+	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1);
+	commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
+	record_phase(s, PH_COLLIDE + 1);
+	return SPH_OK;
+}
+
+static uint32_t buffer_parity(const SphSim *s) {
+	return (uint32_t)s->pos.cur | (uint32_t)s->prev.cur << 1 | (uint32_t)s->vel.cur << 2 | (uint32_t)s->acc.cur << 3 | (uint32_t)s->dens.cur << 4 |
+	       (uint32_t)s->press.cur << 5 | (uint32_t)s->id.cur << 6 | (uint32_t)s->cellOf.cur << 7;
+}
+static void set_buffer_parity(SphSim *s, uint32_t p) {
+	s->pos.cur = p & 1;
+	s->prev.cur = (p >> 1) & 1;
+	s->vel.cur = (p >> 2) & 1;
+	s->acc.cur = (p >> 3) & 1;
+	s->dens.cur = (p >> 4) & 1;
+	s->press.cur = (p >> 5) & 1;
+	s->id.cur = (p >> 6) & 1;
+	s->cellOf.cur = (p >> 7) & 1;
+}
+
 // ---- the hot path -------------------------------------------------------------------------------
 int sph_step(SphHandle s, float dt) {
 	CHECK_HANDLE(s);
@@ -1101,29 +1157,57 @@ int sph_step(SphHandle s, float dt) {
 		if (longest) s->sweepCap = std::min(1024u, std::max(96u, ((longest + longest / 4 + 31u) / 32u) * 32u));
 		s->lagPending = false;
 	}
-	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
 	const PairParams k = pair_params(s, dt);
 	const unsigned nb = blocks_for(s->hostN);
 	const float invDt = 1.0f / dt; // demo4.cpp:287
 	const float2 force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y); // gravity + externalForce, :306
 
-	record_phase(s, 0);
-	begin_step_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
-	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
-	s->accFrom = 0xFFFFFFFFu;
-	record_phase(s, PH_INTEGRATE + 1);
-	run_viscosity(s, k, nb);
-	record_phase(s, PH_VISCOSITY + 1);
-	rc = launch_grid_build(s, dt, true, false, true);
-	if (rc != SPH_OK) return rc;
-	if (exact) launch_density<Exact>(s, k, nb);
-	else launch_density<Fast>(s, k, nb);
-	record_phase(s, PH_DENSITY + 1);
-	run_delta(s, k, nb);
-	record_phase(s, PH_DELTA + 1);
-	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1);
-	commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
-	record_phase(s, PH_COLLIDE + 1);
+	// Steady state (nothing appended since the last step, no per-phase timing, one GPU): the ~30
+	// launches of a step are replayed from a CUDA graph, which removes the launch gaps that dominate
+	// small scenes.  Kernel arguments depend on which half of each double buffer is current, so graphs
+	// are cached per buffer parity, staging capacity, dt, force and parameters.
+	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->cfg.world_size == 1 && s->steps >= 2;
+	bool replayed = false;
+	if (graphable) {
+		StepGraphKey key;
+		memset(&key, 0, sizeof(key));
+		key.parity = buffer_parity(s);
+		key.sweepCap = s->sweepCap;
+		key.nb = nb;
+		key.nbodies = (uint32_t)s->bodies.size();
+		key.force = force;
+		key.k = k;
+		StepGraph *g = nullptr;
+		for (StepGraph &c : s->graphs)
+			if (memcmp(&c.key, &key, sizeof(key)) == 0) g = &c;
+		if (!g) {
+			if (s->graphs.size() >= 8) { // parameters keep changing: drop the oldest
+				cudaGraphExecDestroy(s->graphs.front().exec);
+				s->graphs.erase(s->graphs.begin());
+			}
+			cudaGraph_t graph = nullptr;
+			CU(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+			rc = enqueue_step(s, dt, k, nb, force, invDt);
+			const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+			if (rc != SPH_OK) return rc;
+			if (ce != cudaSuccess) return fail(s, SPH_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+			StepGraph made;
+			made.key = key;
+			made.parityAfter = buffer_parity(s);
+			CU(s, cudaGraphInstantiate(&made.exec, graph, 0));
+			cudaGraphDestroy(graph);
+			set_buffer_parity(s, key.parity); // capture only recorded the launches: the state is still "before the step"
+			s->graphs.push_back(made);
+			g = &s->graphs.back();
+		}
+		CU(s, cudaGraphLaunch(g->exec, s->stream));
+		set_buffer_parity(s, g->parityAfter);
+		replayed = true;
+	}
+	if (!replayed) {
+		rc = enqueue_step(s, dt, k, nb, force, invDt);
+		if (rc != SPH_OK) return rc;
+	}
 	CU(s, cudaGetLastError());
 	s->steps++;
 	s->steppedOnce = true;

@@ -230,22 +230,36 @@ class ParticleSimulation:
         self._check(self._lib.sph_local_particle_count(self._h, C.byref(out)))
         return out.value
 
-    def read_owned(self, records=True, render=False, capacity=None):
-        """ids (+ ParticleData records, + positions/colours) of the particles this rank owns."""
-        cap = int(capacity or self.config.max_particles)
-        ids = np.zeros(cap, np.uint32)
-        rec = np.zeros((cap, 12), np.float32) if records else None
-        pos = np.zeros((cap, 2), np.float32) if render else None
-        col = np.zeros((cap, 4), np.float32) if render else None
+    def read_owned(self, records=True, render=False, capacity=None, buffers=None):
+        """ids (+ ParticleData records, + positions/colours) of the particles this rank owns.
+        `buffers` = dict from owned_buffers() to reuse (pinned) host memory across calls."""
+        if buffers is None:
+            buffers = self.owned_buffers(records=records, render=render, capacity=capacity, pinned=False)
+        ids, rec, pos, col = buffers["ids"], buffers.get("records"), buffers.get("positions"), buffers.get("colors")
         n = C.c_uint64()
-        self._check(self._lib.sph_read_owned(self._h, ids.ctypes.data, rec.ctypes.data if records else None, 48, pos.ctypes.data if render else None, 8,
-                                             col.ctypes.data if render else None, 16, C.byref(n)))
+        self._check(self._lib.sph_read_owned(self._h, ids.ctypes.data, rec.ctypes.data if (records and rec is not None) else None, 48,
+                                             pos.ctypes.data if (render and pos is not None) else None, 8,
+                                             col.ctypes.data if (render and col is not None) else None, 16, C.byref(n)))
         k = n.value
         out = {"ids": ids[:k]}
-        if records:
+        if records and rec is not None:
             out["records"] = rec[:k]
-        if render:
+        if render and pos is not None:
             out["positions"], out["colors"] = pos[:k], col[:k]
+        return out
+
+    def owned_buffers(self, records=True, render=False, capacity=None, pinned=True):
+        """Host arrays for read_owned (page-locked when pinned=True; keep the dict alive while in use)."""
+        cap = int(capacity or self.config.max_particles)
+        make = (lambda shape, dt: pinned_empty(shape, dt)) if pinned else (lambda shape, dt: (np.empty(shape, dt), None))
+        out, owners = {}, []
+        for name, shape, dt, want in (("ids", (cap,), np.uint32, True), ("records", (cap, 12), np.float32, records),
+                                      ("positions", (cap, 2), np.float32, render), ("colors", (cap, 4), np.float32, render)):
+            if want:
+                arr, own = make(shape, dt)
+                out[name] = arr
+                owners.append(own)
+        out["_owners"] = owners
         return out
 
     def grid_dims(self):
