@@ -513,6 +513,19 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 	for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
 	return v;
 }
+// Both components of a particle's own change with 6 shuffles instead of 10: after the first exchange
+// lanes 0-15 carry x and lanes 16-31 carry y, each half then runs the remaining four butterfly stages.
+// The additions are the ones lane 0 performs in butterfly_sum (v_l + v_(l^o), same order of stages), so
+// the sums are bit-identical to it.  Valid in lane 0 only.
+__device__ __forceinline__ float2 butterfly_sum2_lane0(float x, float y, uint32_t lane) {
+	const bool lower = lane < 16u;
+	const float other = __shfl_xor_sync(0xffffffffu, lower ? y : x, 16);
+	float v = __fadd_rn(lower ? x : y, other);
+#pragma unroll
+	for (int o = 8; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+	const float ysum = __shfl_sync(0xffffffffu, v, 16);
+	return make_float2(v, ysum);
+}
 
 // Per particle i of the cell the candidate loop runs in two stages.  Stage 1 tests every candidate
 // against h (5 flops) and compacts the ones in range into a queue (ballot + popc); stage 2 evaluates
@@ -615,8 +628,9 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 					}
 				}
 			}
-			ax = butterfly_sum(ax);
-			ay = butterfly_sum(ay);
+			const float2 own = butterfly_sum2_lane0(ax, ay, lane);
+			ax = own.x;
+			ay = own.y;
 			__syncwarp();
 			if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
 				if (STAGED) {
