@@ -17,9 +17,10 @@ ap.add_argument("--steps", type=int, default=300)
 ap.add_argument("--every", type=int, default=50)
 ap.add_argument("--solver", default="gs")
 ap.add_argument("--relaxation", type=float, default=1.0)
+ap.add_argument("--flags", type=int, default=0, help="SPH_FLAG_* (2 = no CUDA graphs)")
 a = ap.parse_args()
 g = a.gravity if a.gravity is not None else -10.0 * min(1.0, 5.34375 / (a.nx * a.spacing))
-sim = scenes.fill_block(scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, g), relaxation=a.relaxation,
+sim = scenes.fill_block(scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, g), relaxation=a.relaxation, flags=a.flags,
                                            solver=SPH_SOLVER_GATHER if a.solver == "gather" else SPH_SOLVER_COLORED_GS))
 n = sim.GetParticleCount()
 dt = float(np.float32(1) / np.float32(60))
