@@ -188,14 +188,15 @@ def run_ours(args):
     flush.fill_(1)
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     sim.mark(0)
     for _ in range(args.steps):
         sim.Update(DT)
     sim.mark(1)
     ms = sim.elapsed_ms(0, 1)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if not args.no_clock_sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler disabled"]}
     ms = all_max(ms)
     stats = sim.GetStats()  # raises if a capacity flag was set on the device
     value = n_total * args.steps / (ms * 1e-3)
@@ -390,6 +391,7 @@ def main():
     ap.add_argument("--relaxation", type=float, default=0.0, help="gather only: omega")
     ap.add_argument("--sweep-capacity", type=int, default=0)
     ap.add_argument("--halo-rows", type=int, default=0)
+    ap.add_argument("--no-clock-sampler", action="store_true", help="experiment: do not poll NVML during the timed region")
     ap.add_argument("--nx-total", type=int, default=0, help="edge of the whole block, overriding the weak-scaling rule")
     ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")
     args = ap.parse_args()

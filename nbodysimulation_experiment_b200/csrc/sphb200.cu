@@ -1151,10 +1151,11 @@ int sph_step(SphHandle s, float dt) {
 	int rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
 	if (s->sweepAdaptive && s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
-		// shared-memory staging sized to the longest candidate list seen a step or two ago (+25 %);
-		// anything longer still works through the L2 path, so a stale value only costs speed
+		// shared-memory staging sized to twice the longest candidate list seen recently: a host that
+		// enqueues hundreds of steps ahead of the device (graph replay costs ~7 us per step) only sees
+		// old counts, and blocks that outgrow the staging fall back to the much slower L2 path
 		const uint32_t longest = s->hCtrLag->maxNbr;
-		if (longest) s->sweepCap = std::min(1024u, std::max(96u, ((longest + longest / 4 + 31u) / 32u) * 32u));
+		if (longest) s->sweepCap = std::min(1024u, std::max(192u, ((2u * longest + 31u) / 32u) * 32u));
 		s->lagPending = false;
 	}
 	const PairParams k = pair_params(s, dt);
