@@ -307,7 +307,7 @@ def oracle_scene(nx, spacing, gravity, threads, mode):
     return sim
 
 
-def cpu_baseline(nx, spacing, gravity, relaxation, budget_s=20.0):
+def cpu_baseline(nx, spacing, gravity, relaxation, budget_s=12.0):
     """The oracle in the reference's own multithreaded mode (in-place pair updates, thread-pool split of
     threading.h:111-129) on all host cores, on a bounded sample of the same scene."""
     from oracle_lib import MODE_GS_INDEX, build_oracle
@@ -319,7 +319,7 @@ def cpu_baseline(nx, spacing, gravity, relaxation, budget_s=20.0):
     n = sim.n
     sim.advance(DT, 1)
     t = sim.advance_timed(DT, 1)
-    steps = int(max(2, min(64, budget_s / max(t, 1e-3))))
+    steps = int(max(2, min(1024, budget_s / max(t, 1e-3))))
     secs = sim.advance_timed(DT, steps)
     sim.close()
     return {"value": n * steps / secs, "unit": UNIT, "cores": cores, "kind": "port",

@@ -9,6 +9,7 @@ Both expose the same verbs, so `CpuSim` wraps either one behind one Python class
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -28,7 +29,8 @@ vp = C.c_void_p
 
 def build_oracle():
     """Compile the checker (never the product).  Safe to call repeatedly."""
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle", "ref"], check=True)
+    # make's chatter goes to stderr: bench.py promises exactly one JSON line on stdout
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle", "ref"], check=True, stdout=sys.stderr)
 
 
 def _load(path):
