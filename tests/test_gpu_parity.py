@@ -369,3 +369,116 @@ def test_colored_solver_tracks_reference_energy(pkg):
     assert np.abs(a[:, 0:2].mean(0) - b[:, 0:2].mean(0)).max() < 2e-2   # centre of mass
     assert abs(a[:, 8].mean() / b[:, 8].mean() - 1.0) < 0.05            # mean density
     gpu.close()
+
+
+# ---- edge cases the reference guards with asserts ---------------------------
+def test_empty_and_single_particle(pkg):
+    sim = pkg.ParticleSimulation()
+    sim.AddPlane((0.0, 1.0), -2.8125)
+    sim.Update(DT)  # nothing to do, must not fail
+    assert sim.GetParticleCount() == 0 and sim.particles().shape == (0, 12)
+    sim.SetGravity((0.0, -10.0))
+    sim.AddParticle((0.5, 0.25), (3.0, 0.0))
+    cpu = CpuSim("oracle", mode=MODE_COLORED)
+    cpu.add_plane(0.0, 1.0, -2.8125)
+    cpu.set_gravity(0.0, -10.0)
+    cpu.add_particle(0.5, 0.25, 3.0, 0.0)
+    for _ in range(30):
+        sim.Update(DT)
+        cpu.advance(DT)
+    assert_bits_equal(sim.particles(), cpu.particles(), "one particle: acceleration consumed once, then free fall")
+    st = sim.GetStats()
+    assert (st.min_particle_neighbor_count, st.max_particle_neighbor_count) == (1, 1)  # itself (demo4.cpp:183-206)
+    sim.close()
+
+
+def test_capacities_are_errors_not_asserts(pkg):
+    sim = pkg.ParticleSimulation(max_particles=100)
+    sim.AddParticles(np.zeros((100, 2), np.float32))
+    with pytest.raises(pkg.SphError) as e:
+        sim.AddParticle((0.0, 0.0))
+    assert e.value.code == -2
+    for _ in range(100):  # kSPHMaxBodyCount, sph.h:71
+        sim.AddCircle((0.0, 0.0), 0.1)
+    with pytest.raises(pkg.SphError) as e:
+        sim.AddCircle((0.0, 0.0), 0.1)
+    assert e.value.code == -2
+    with pytest.raises(pkg.SphError):
+        sim.AddPolygon(np.zeros((9, 2), np.float32))  # kMaxScenarioPolygonCount, sph.h:161
+    for _ in range(8):  # kSPHMaxEmitterCount, sph.h:72
+        sim.AddEmitter((0, 0), (1, 0), 0.3, 1.0, 15.0, 1.0)
+    with pytest.raises(pkg.SphError) as e:
+        sim.AddEmitter((0, 0), (1, 0), 0.3, 1.0, 15.0, 1.0)
+    assert e.value.code == -2
+    sim.close()
+
+
+def test_out_of_domain_positions_clamp_into_edge_cells(pkg):
+    """sph.h:459-460: the grid (9.9 x 5.4) is smaller than the domain and everything outside is
+    clamped into the edge cells; also more than the reference's 500 particles per cell."""
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.uniform(-8, 8, (3000, 2)), rng.uniform(-0.1, 0.1, (700, 2)) + [1.15, 1.16]]).astype(np.float32)
+    sim = pkg.ParticleSimulation(solver=pkg.SPH_SOLVER_GATHER)
+    cpu = CpuSim("oracle", mode=MODE_JACOBI)
+    sim.AddParticles(pts)
+    for x, y in pts:
+        cpu.add_particle(float(x), float(y), 0.0, 0.0)
+    sim.RunPass(pkg._lib.PASS_GRID, DT)
+    cpu.pass_update_grid()
+    cpu.pass_neighbor_search()
+    assert np.array_equal(sim.cell_of_particle(), cpu.cell_of_particle())
+    assert np.array_equal(sim.cell_counts(), cpu.cell_counts())
+    assert sim.cell_counts().max() > 500
+    sim.RunPass(pkg._lib.PASS_DENSITY, DT)
+    cpu.pass_density()
+    assert_bits_equal(sim.particles()[:, 8:12], cpu.particles()[:, 8:12], "density with a 700-particle cell")
+    sim.close()
+
+
+def test_parameters_and_external_force(pkg):
+    """SetParams (10x viscosity, different stiffness), AddExternalForces / ClearExternalForce."""
+    for solver, mode in ((pkg.SPH_SOLVER_COLORED_GS, MODE_COLORED), (pkg.SPH_SOLVER_GATHER, MODE_JACOBI)):
+        sim = pkg.ParticleSimulation(solver=solver)
+        cpu = CpuSim("oracle", mode=mode)
+        sim.LoadScenario(3, seed=4)
+        cpu.load_scenario(3, 4)
+        p = sim.GetParams()
+        p.linear_viscosity, p.quadratic_viscosity, p.stiffness, p.near_stiffness = 5.0, 3.0, 0.4, 8.0
+        sim.SetParams(p)
+        cpu.put_params(sim.params_array())
+        sim.AddExternalForces((1.5, 0.5))
+        cpu.add_external_force(1.5, 0.5)
+        for k in range(20):
+            if k == 10:
+                sim.ClearExternalForce()
+                cpu.clear_external_force()
+            sim.Update(DT)
+            cpu.advance(DT)
+        assert_bits_equal(sim.particles(), cpu.particles(), f"solver {solver}")
+        sim.close()
+
+
+def test_graph_replay_is_bit_identical_to_plain_launches(pkg):
+    runs = []
+    for flags in (0, pkg._lib.SPH_FLAG_NO_GRAPHS):
+        s = pkg.ParticleSimulation(flags=flags)
+        s.LoadScenario(1, seed=2)
+        for _ in range(25):
+            s.Update(DT)
+        runs.append(s.particles())
+        s.close()
+    assert_bits_equal(runs[0], runs[1], "graph vs plain")
+
+
+def test_two_gpu_strips_match_one_gpu_bitwise():
+    """Runs tools/mgpu_check.py under torchrun when the box has two GPUs (the round-end box has one)."""
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+                          os.path.join(root, "tools", "mgpu_check.py"), "--nx", "256", "--steps", "40"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "MGPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
