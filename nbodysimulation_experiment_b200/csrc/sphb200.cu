@@ -93,7 +93,7 @@ enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DEN
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
 struct StepGraphKey {
-	uint32_t parity, sweepCap, nb, nbodies;
+	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, pad;
 	float2 force;
 	PairParams k;
 };
@@ -346,17 +346,14 @@ void record_phase(SphSim *s, int idx) {
 }
 
 // ---- the grid build shared by sph_step and sph_run_pass(GRID) ------------------------------
-// migration + halo in one neighbour exchange (fixed-size messages, count in the header), then file
-// what arrived behind the local particles
-int exchange_halos(SphSim *s) {
+// Message size: NCCL needs it on the host, the record counts only exist on the device.  All ranks
+// therefore ship the same fixed number of records per message, re-agreed every kHaloResizeEvery steps
+// as 1.5 x the largest count any rank packed since (one stream sync + a 4-byte all-reduce).  The
+// first messages carry the whole buffer.  A count above the agreed size raises the overflow flag on
+// the sender (note_peak_kernel) and on the receiver (header count > records shipped).
+int maybe_resize_halo(SphSim *s) {
 	const StripDesc &sd = s->strip;
-	if (!s->comm) return fail(s, SPH_ERR_STATE, "sph_comm_init was not called on this multi-GPU handle");
 	NcclApi &nc = g_nccl;
-	// Message size: NCCL needs it on the host, the record counts only exist on the device.  All ranks
-	// therefore ship the same fixed number of records per message, re-agreed every kHaloResizeEvery
-	// steps as 1.5 x the largest count any rank packed since (one stream sync + a 4-byte all-reduce).
-	// The first messages carry the whole buffer.  A count above the agreed size raises the overflow
-	// flag on the sender (pack) and on the receiver (header count > records shipped).
 	if (s->exchanges > 0 && s->exchanges % kHaloResizeEvery == 0) {
 		int rca = nc.AllReduce(s->dPeak, s->dPeak + 1, 1, kNcclUint32, kNcclMax, s->comm, s->stream);
 		if (rca != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce failed: %s", nc.GetErrorString(rca));
@@ -368,6 +365,15 @@ int exchange_halos(SphSim *s) {
 		s->haloMsgRecords = (uint32_t)std::min<uint64_t>(sd.haloCap, want);
 	}
 	s->exchanges++;
+	return SPH_OK;
+}
+
+// migration + halo in one neighbour exchange (fixed-size messages, count in the header), then file
+// what arrived behind the local particles
+int exchange_halos(SphSim *s) {
+	const StripDesc &sd = s->strip;
+	if (!s->comm) return fail(s, SPH_ERR_STATE, "sph_comm_init was not called on this multi-GPU handle");
+	NcclApi &nc = g_nccl;
 	const size_t msgBytes = sizeof(HaloBuffer) + (size_t)s->haloMsgRecords * sizeof(HaloRecord);
 	note_peak_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1], s->dPeak, s->haloMsgRecords, s->dCtr);
 	int rc = nc.GroupStart();
@@ -1167,7 +1173,11 @@ int sph_step(SphHandle s, float dt) {
 	// launches of a step are replayed from a CUDA graph, which removes the launch gaps that dominate
 	// small scenes.  Kernel arguments depend on which half of each double buffer is current, so graphs
 	// are cached per buffer parity, staging capacity, dt, force and parameters.
-	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->cfg.world_size == 1 && s->steps >= 2;
+	if (s->cfg.world_size > 1) {
+		rc = maybe_resize_halo(s);
+		if (rc != SPH_OK) return rc;
+	}
+	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2;
 	bool replayed = false;
 	if (graphable) {
 		StepGraphKey key;
@@ -1176,6 +1186,7 @@ int sph_step(SphHandle s, float dt) {
 		key.sweepCap = s->sweepCap;
 		key.nb = nb;
 		key.nbodies = (uint32_t)s->bodies.size();
+		key.haloMsgRecords = s->haloMsgRecords;
 		key.force = force;
 		key.k = k;
 		StepGraph *g = nullptr;
@@ -1261,6 +1272,10 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 			predict_only_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), dt);
 			break;
 		case SPH_PASS_GRID:
+			if (s->cfg.world_size > 1) {
+				rc = maybe_resize_halo(s);
+				if (rc != SPH_OK) return rc;
+			}
 			begin_step_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
 			rc = launch_grid_build(s, dt, false, true, false);
 			if (rc != SPH_OK) return rc;
