@@ -1177,7 +1177,9 @@ int sph_step(SphHandle s, float dt) {
 		rc = maybe_resize_halo(s);
 		if (rc != SPH_OK) return rc;
 	}
-	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2;
+	// (strips: NCCL send/recv inside a captured stream dead-locked on this stack (NCCL 2.28.9, driver 580), so
+	// multi-GPU steps are launched kernel by kernel)
+	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2 && s->cfg.world_size == 1;
 	bool replayed = false;
 	if (graphable) {
 		StepGraphKey key;
