@@ -44,8 +44,8 @@ BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
 # algorithmic HBM bytes per particle of each phase (DESIGN.md "kernels")
 PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "reorder": 44, "density": 16, "delta": 24, "collide_velocity": 32}
-# begin, integrate, 9 x viscosity sweep, predict_key, 3 x scan, colour lists, scatter_ids, reorder, density, 9 x delta sweep, collide_velocity, commit
-KERNELS_PER_STEP = {"gs": 30, "gather": 13}
+# integrate, 9 x viscosity sweep, predict_key, scan (tiles, sums, add+colour lists), scatter_ids, reorder, density, 9 x delta sweep, collide_velocity
+KERNELS_PER_STEP = {"gs": 27, "gather": 11}
 
 
 def scene_gravity(nx, spacing, scaled):

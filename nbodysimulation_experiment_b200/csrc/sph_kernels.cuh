@@ -59,9 +59,16 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // ---- phase 1: integrate forces (demo4.cpp:302-312) --------------------------------------
 // a += g + fext; v += a*dt; a = 0.  Only particles added since the last step carry a non-zero
 // acceleration (demo4.cpp:146), so `acc` is read from index accFrom on and zeroed.
-__global__ void __launch_bounds__(SPH_THREADS) integrate_kernel(const Counters *__restrict__ ctr, float2 *__restrict__ vel,
+// Block 0 also opens the step: it resets the statistics that are per step in the reference
+// (demo4.cpp:369-370); nothing else in this kernel touches them.
+__global__ void __launch_bounds__(SPH_THREADS) integrate_kernel(Counters *__restrict__ ctr, float2 *__restrict__ vel,
                                                                float2 *__restrict__ acc, uint32_t accFrom, float2 force, float dt) {
 	const uint32_t n = ctr->n;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		ctr->minNbr = 0xffffffffu;
+		ctr->maxNbr = 0;
+		ctr->pairCandidates = 0ull;
+	}
 	SPH_WARP_LOOP(i, n) {
 		if (i >= n) continue;
 		float2 a = make_float2(0.0f, 0.0f);
@@ -337,6 +344,33 @@ __global__ void __launch_bounds__(SPH_THREADS) scan_add_kernel(uint32_t *__restr
 		if (first + k < nCells) cellStart[first + k] += off;
 }
 
+// scan_add_kernel and color_lists_kernel in one pass over the cells (coloured solver): the tile offset
+// is added, and occupied cells are filed under their colour.  A cell's count is start[c+1]-start[c];
+// the next cell may belong to the next tile, whose offset is added here by hand.
+__global__ void __launch_bounds__(SPH_THREADS) scan_add_lists_kernel(GridDesc g, uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ tileSums,
+                                                                    const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ colorCount,
+                                                                    uint32_t *__restrict__ colorList, uint32_t listStride) {
+	const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; // blockDim divides SPH_SCAN_TILE: one tile offset per block
+	int color = -1;
+	if (c < g.nCells) {
+		cellStart[c] += tileSums[c / SPH_SCAN_TILE];
+		if (cellCount[c] > 0) {
+			const uint32_t yl = c / (uint32_t)g.gx, cx = c - yl * (uint32_t)g.gx;
+			color = (int)(((yl + (uint32_t)g.rowLo) % 3u) * 3u + cx % 3u);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 9; ++k) {
+		const uint32_t mask = __ballot_sync(0xffffffffu, color == k);
+		if (!mask) continue;
+		const int leader = __ffs(mask) - 1;
+		uint32_t at = 0;
+		if ((int)lane_id() == leader) at = atomicAdd(&colorCount[k], (uint32_t)__popc(mask));
+		at = __shfl_sync(0xffffffffu, at, leader);
+		if (color == k) colorList[(uint32_t)k * listStride + at + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u))] = c;
+	}
+}
+
 // ---- phase 4c: drop each id at (cell start + arrival rank) ----------------------------------
 __global__ void __launch_bounds__(SPH_THREADS) scatter_ids_kernel(GridDesc g, const Counters *__restrict__ ctr, const uint32_t *__restrict__ cellNew,
                                                                  const uint32_t *__restrict__ rank, const uint32_t *__restrict__ id,
@@ -370,11 +404,16 @@ __global__ void __launch_bounds__(SPH_THREADS) reorder_kernel(GridDesc g, Counte
 		const uint32_t key = ((c >> 16) - (uint32_t)g.rowLo) * (uint32_t)g.gx + (c & 0xffffu);
 		const uint32_t lo = cellStart[key], hi = cellStart[key + 1];
 		const uint32_t me = id[i];
-		uint32_t r = 0;
-		for (uint32_t s = lo; s < hi; ++s) r += (slotId[s] < me) ? 1u : 0u;
+		const float2 p = pos[i], q = prev[i]; // issued before the ranking loop so their latency overlaps it
+		uint32_t r = 0, s = lo;
+		for (; s + 4 <= hi; s += 4) { // four independent loads in flight
+			const uint32_t a0 = slotId[s], a1 = slotId[s + 1], a2 = slotId[s + 2], a3 = slotId[s + 3];
+			r += (a0 < me ? 1u : 0u) + (a1 < me ? 1u : 0u) + (a2 < me ? 1u : 0u) + (a3 < me ? 1u : 0u);
+		}
+		for (; s < hi; ++s) r += (slotId[s] < me) ? 1u : 0u;
 		const uint32_t dst = lo + r;
-		posOut[dst] = pos[i];
-		prevOut[dst] = prev[i];
+		posOut[dst] = p;
+		prevOut[dst] = q;
 		idOut[dst] = me;
 		cellOut[dst] = c;
 		occMin = min(occMin, hi - lo);
@@ -720,6 +759,11 @@ __global__ void __launch_bounds__(SPH_THREADS) collide_velocity_kernel(Counters 
 			const float2 q = prev[i];
 			vel[i] = make_float2(__fmul_rn(__fsub_rn(p.x, q.x), invDt), __fmul_rn(__fsub_rn(p.y, q.y), invDt));
 		}
+	}
+	// closes the step: every block read nOut above, nobody in this kernel reads n / nSorted
+	if (commit && blockIdx.x == 0 && threadIdx.x == 0) {
+		ctr->n = n;
+		ctr->nSorted = n;
 	}
 }
 

@@ -415,10 +415,12 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	if (timed) record_phase(s, PH_EXCHANGE + 1);
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
-	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
 	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) {
 		cudaMemsetAsync(s->colorCount, 0, 9 * sizeof(uint32_t), s->stream);
-		color_lists_kernel<<<(g.nCells + SPH_THREADS - 1) / SPH_THREADS, SPH_THREADS, 0, s->stream>>>(g, s->cellStart, s->colorCount, s->colorList, s->listStride);
+		scan_add_lists_kernel<<<(g.nCells + SPH_THREADS - 1) / SPH_THREADS, SPH_THREADS, 0, s->stream>>>(g, s->cellStart, s->tileSums, s->cellCount, s->colorCount,
+		                                                                                           s->colorList, s->listStride);
+	} else {
+		scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
 	}
 	if (timed) record_phase(s, PH_SCAN + 1);
 	scatter_ids_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->cellNew, s->rank, s->id.in(), s->cellStart, s->slotId);
@@ -1110,8 +1112,7 @@ extern "C" int sph_load_scenario(SphHandle s, int idx, int seed) {
 static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, float2 force, float invDt) {
 	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
 	record_phase(s, 0);
-	begin_step_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
-	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
+	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt); // also opens the step
 	s->accFrom = 0xFFFFFFFFu;
 	record_phase(s, PH_INTEGRATE + 1);
 	run_viscosity(s, k, nb);
@@ -1123,8 +1124,7 @@ static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, f
 	record_phase(s, PH_DENSITY + 1);
 	run_delta(s, k, nb);
 	record_phase(s, PH_DELTA + 1);
-	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1);
-	commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
+	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1); // also closes the step
 	record_phase(s, PH_COLLIDE + 1);
 	return SPH_OK;
 }
