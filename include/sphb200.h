@@ -78,7 +78,7 @@ typedef struct SphConfig {
 	int32_t rank;
 	int32_t world_size;
 	uint64_t halo_capacity;  /* particles per direction per step the exchange buffers hold (0 = max_particles/4) */
-	int32_t halo_rows;       /* ghost rows kept on each side of the strip (0 = 9) */
+	int32_t halo_rows;       /* ghost rows kept on each side of the strip (0 = 7) */
 	int32_t reserved0;
 } SphConfig;
 

@@ -1,9 +1,12 @@
 // CUDA kernels of the SPH step (sm_100a).  One step is, in the reference's phase order
 // (demo4.cpp:286-451):
 //
-//   integrate -> viscosity gather (previous step's grid) -> predict + cell key + histogram
-//   -> exclusive scan -> id scatter -> canonical reorder -> density gather -> displacement gather
-//   -> collide + velocity
+//   integrate -> viscosity (previous step's grid) -> predict + cell key + histogram [-> strip exchange]
+//   -> exclusive scan (+ colour lists) -> id scatter -> canonical reorder -> density gather
+//   -> pressure displacement -> collide + velocity
+//
+// Viscosity and displacement are 9-colour in-place Gauss-Seidel sweeps by default (color_sweep_kernel)
+// or plain gathers (viscosity_kernel / delta_kernel) with SPH_SOLVER_GATHER.
 //
 // Data layout: cell-sorted SoA.  `pos/prev/vel` are float2, `cellOf` is the packed (cy<<16|cx) cell
 // of each sorted particle, `id` its creation index, `cellStart` the exclusive prefix over the
@@ -26,7 +29,7 @@ struct Counters {
 	uint32_t nSorted;  // particles covered by cellStart / cellOf (the previous step's grid)
 	uint32_t nIn;      // n + particles received from neighbour strips this step
 	uint32_t nOut;     // particles kept by this step's grid build (= cellStart[nCells])
-	uint32_t sendDown, sendUp; // halo/migration records packed for the lower / upper strip
+	uint32_t reserved0, reserved1;
 	uint32_t lost;     // particles that left the local rows with nowhere to go
 	uint32_t overflow; // capacity overflow flags
 	uint32_t minNbr, maxNbr, minCell, maxCell;
@@ -490,29 +493,6 @@ __global__ void __launch_bounds__(SPH_THREADS) delta_kernel(GridDesc g, PairPara
 // staging capacity take the same algorithm through L2 (__ldcg/__stcg).
 #define SPH_SWEEP_WARPS 4
 
-// occupied cells of each colour, rebuilt with the grid (order inside a list is irrelevant: the
-// footprints of one colour are disjoint)
-__global__ void __launch_bounds__(SPH_THREADS) color_lists_kernel(GridDesc g, const uint32_t *__restrict__ cellStart, uint32_t *__restrict__ colorCount,
-                                                                 uint32_t *__restrict__ colorList, uint32_t listStride) {
-	const uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-	const uint32_t c = base + lane_id();
-	int color = -1;
-	if (c < g.nCells && cellStart[c + 1] > cellStart[c]) {
-		const uint32_t yl = c / (uint32_t)g.gx, cx = c - yl * (uint32_t)g.gx;
-		color = (int)(((yl + (uint32_t)g.rowLo) % 3u) * 3u + cx % 3u);
-	}
-#pragma unroll
-	for (int k = 0; k < 9; ++k) {
-		const uint32_t mask = __ballot_sync(0xffffffffu, color == k);
-		if (!mask) continue;
-		const int leader = __ffs(mask) - 1;
-		uint32_t at = 0;
-		if ((int)lane_id() == leader) at = atomicAdd(&colorCount[k], (uint32_t)__popc(mask));
-		at = __shfl_sync(0xffffffffu, at, leader);
-		if (color == k) colorList[(uint32_t)k * listStride + at + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u))] = c;
-	}
-}
-
 enum { SWEEP_DELTA = 0, SWEEP_VISCOSITY = 1 };
 
 template <class M>
@@ -772,13 +752,12 @@ __global__ void commit_kernel(Counters *ctr) {
 	ctr->nSorted = ctr->nOut;
 }
 
-// per-step reset of the statistics that are per-step in the reference (demo4.cpp:369-370)
+// per-step reset of the statistics that are per-step in the reference (demo4.cpp:369-370); the full
+// step does this inside integrate_kernel, single passes (sph_run_pass) use this
 __global__ void begin_step_kernel(Counters *ctr) {
 	ctr->minNbr = 0xffffffffu;
 	ctr->maxNbr = 0;
 	ctr->pairCandidates = 0ull;
-	ctr->sendDown = 0;
-	ctr->sendUp = 0;
 }
 
 // ---- readback / injection -----------------------------------------------------------------------

@@ -486,7 +486,7 @@ void launch_delta(SphSim *s, const PairParams &k, unsigned nb) {
 	delta_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->press.in(), s->cellOf.in(), s->cellStart, s->pos.out());
 }
 
-constexpr int kDefaultHaloRows = 9; // DESIGN.md "multi-GPU": an edge error moves <= 3 rows inward per sweep (density+displacement, viscosity) + 3 rows margin
+constexpr int kDefaultHaloRows = 7; // DESIGN.md "multi-GPU": an edge error moves <= 3 rows inward per sweep (density+displacement, viscosity) = 6, + 1
 
 // (re)allocates everything sized by the local window of grid rows
 int configure_strip(SphSim *s, int ownLo, int ownHi) {

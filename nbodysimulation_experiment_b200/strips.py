@@ -8,7 +8,7 @@ by the CPU (gloo) tests of the multi-rank protocol.  Nothing here touches partic
 """
 import numpy as np
 
-DEFAULT_HALO_ROWS = 9  # keep in sync with kDefaultHaloRows in csrc/sphb200.cu
+DEFAULT_HALO_ROWS = 7  # keep in sync with kDefaultHaloRows in csrc/sphb200.cu
 
 
 def cell_rows(y, half_height, cell, grid_y):

@@ -28,7 +28,7 @@ from nbodysimulation_experiment_b200 import strips  # noqa: E402
 
 WORLD = 2
 GRID_Y, CELL, HALF_H = 18, float(np.float32(6.0) * np.float32(0.05)), 5.625 / 2
-HALO = 3  # the 18-row reference grid is too short for the default 9-row halo
+HALO = 3  # the 18-row reference grid is too short for the default 7-row halo
 
 
 def free_port():
@@ -118,9 +118,9 @@ def test_split_and_windows():
     s = strips.split_rows(1366, 3072, 8)
     assert s[0][0] == 0 and s[-1][1] == 3072 and all(a[1] == b[0] for a, b in zip(s, s[1:]))
     assert all(hi - lo >= strips.DEFAULT_HALO_ROWS for lo, hi in s)
-    assert strips.window((171, 342), 9, 3072, 8) == (162, 351)
-    assert strips.window((0, 171), 9, 3072, 8) == (0, 180)
-    assert strips.window((0, 3072), 9, 3072, 1) == (0, 3072)
+    assert strips.window((171, 342), 7, 3072, 8) == (164, 349)
+    assert strips.window((0, 171), 7, 3072, 8) == (0, 178)
+    assert strips.window((0, 3072), 7, 3072, 1) == (0, 3072)
     with pytest.raises(ValueError):
         strips.merge_owned([(np.array([0, 1]), np.zeros((2, 12))), (np.array([1, 2]), np.zeros((2, 12)))], 4)
 
