@@ -39,6 +39,9 @@ WORKLOADS = {
     # fixed-dt relaxation (the reference's as much as ours) produces NaNs by step ~250
     "dambreak_1m": dict(nx=1024, spacing=0.1, gravity_scale=True, relaxation=1.0),
     "dambreak_1m_dense": dict(nx=1024, spacing=0.05, gravity_scale=True, relaxation=1.0),
+    # BASELINE.json configs[4] / SURVEY.md 8(d) c5: 2048 x 2048 dense block, 10x viscosity, circles + boxes.
+    # Use --steps 128 --warmup 32: at 10x viscosity the explicit impulses (sph.h:508) diverge after ~250 steps
+    "bodies_4m": dict(nx=2048, spacing=0.05, gravity_scale=True, relaxation=1.0, bodies=True),
 }
 BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
@@ -156,8 +159,9 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
 
     def make(flags=0, which=0):
-        sim = scenes.block_scene(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=relaxation, device=local_rank,
-                                 solver=solver, sweep_capacity=args.sweep_capacity, rank=rank, world_size=world, halo_rows=args.halo_rows)
+        build = scenes.bodies_scene if wl.get("bodies") else scenes.block_scene
+        sim = build(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=relaxation, device=local_rank,
+                    solver=solver, sweep_capacity=args.sweep_capacity, rank=rank, world_size=world, halo_rows=args.halo_rows)
         if world > 1:
             sim.comm_init(uid[which])
             sim.set_strip(*scenes.block_strips(sim, world)[rank])

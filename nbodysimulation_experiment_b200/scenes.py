@@ -71,19 +71,27 @@ def fill_block(sim):
     return sim
 
 
-def bodies_scene(nx, spacing=0.1, seed=1337, **kw):
-    """c5: block + rigid circles and tilted boxes a la "Fun" (sph.h:420-436), 10x viscosity."""
+def bodies_scene(nx, spacing=0.05, seed=1337, **kw):
+    """BASELINE.json configs[4]: a dense block (spacing h/6, the reference's scene-0
+    regime) with 10x viscosity next to rigid bodies a la "Fun" (sph.h:420-436): three circles along its
+    free side, a tilted box above it and a box resting on the floor.  The block starts compressed
+    (rho ~ 27 > rho0), expands into the bodies within a few dozen steps and piles up against them, which
+    skews the candidate counts."""
     sim = block_scene(nx, spacing=spacing, seed=seed, linear_viscosity=5.0, quadratic_viscosity=3.0, **kw)
     w, h = sim.scene["width"], sim.scene["height"]
     s = nx * spacing  # block edge
-    hw, hh = w * 0.5, h * 0.5
-    sim.AddCircle((-hw + 1.6 * s, -hh + 0.20 * s), 0.18 * s)
-    sim.AddCircle((-hw + 2.4 * s, -hh + 0.10 * s), 0.10 * s)
-    sim.AddCircle((-hw + 3.2 * s, -hh + 0.25 * s), 0.20 * s)
-    for (cx, cy, ang, ex, ey) in ((-hw + 2.0 * s, -hh + 0.6 * s, -2.5, 0.45 * s, 0.02 * s), (-hw + 3.0 * s, -hh + 0.45 * s, 2.5, 0.45 * s, 0.02 * s)):
-        a = np.deg2rad(ang)
+    x0, y0 = -w * 0.5 + 0.05, -h * 0.5 + 0.05  # lower-left corner of the block
+    r = 0.08 * s
+    for k in range(3):
+        sim.AddCircle((x0 + s + r + 0.6, y0 + (0.15 + 0.3 * k) * s), r)
+
+    def box(cx, cy, ang_deg, ex, ey):
+        a = np.deg2rad(ang_deg)
         c, sn = np.cos(a), np.sin(a)
         local = np.array([(ex, ey), (-ex, ey), (-ex, -ey), (ex, -ey)])
         verts = np.stack([c * local[:, 0] - sn * local[:, 1] + cx, sn * local[:, 0] + c * local[:, 1] + cy], 1)
         sim.AddPolygon(verts.astype(np.float32))
+
+    box(x0 + 0.5 * s, y0 + s + 0.04 * s + 0.8, -2.5, 0.45 * s, 0.02 * s)  # lid, tilted like the reference's ramps
+    box(x0 + 1.5 * s, y0 + 0.05 * s, 0.0, 0.03 * s, 0.05 * s)             # post on the floor, cf. sph.h:434
     return sim

@@ -18,10 +18,17 @@ ap.add_argument("--every", type=int, default=50)
 ap.add_argument("--solver", default="gs")
 ap.add_argument("--relaxation", type=float, default=1.0)
 ap.add_argument("--flags", type=int, default=0, help="SPH_FLAG_* (2 = no CUDA graphs)")
+ap.add_argument("--bodies", action="store_true", help="BASELINE.json configs[4]: circles + tilted boxes, 10x viscosity")
+ap.add_argument("--viscosity-scale", type=float, default=0.0, help="override: multiply the default linear/quadratic viscosity")
 a = ap.parse_args()
 g = a.gravity if a.gravity is not None else -10.0 * min(1.0, 5.34375 / (a.nx * a.spacing))
-sim = scenes.fill_block(scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, g), relaxation=a.relaxation, flags=a.flags,
-                                           solver=SPH_SOLVER_GATHER if a.solver == "gather" else SPH_SOLVER_COLORED_GS))
+make = scenes.bodies_scene if a.bodies else scenes.block_scene
+sim = scenes.fill_block(make(a.nx, spacing=a.spacing, gravity=(0.0, g), relaxation=a.relaxation, flags=a.flags,
+                             solver=SPH_SOLVER_GATHER if a.solver == "gather" else SPH_SOLVER_COLORED_GS))
+if a.viscosity_scale:
+    p = sim.GetParams()
+    p.linear_viscosity, p.quadratic_viscosity = 0.5 * a.viscosity_scale, 0.3 * a.viscosity_scale
+    sim.SetParams(p)
 n = sim.GetParticleCount()
 dt = float(np.float32(1) / np.float32(60))
 print(f"n {n} gravity {g:.4f} solver {a.solver}", flush=True)
