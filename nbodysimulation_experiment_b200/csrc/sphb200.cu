@@ -93,7 +93,7 @@ enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DEN
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
 struct StepGraphKey {
-	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, pad;
+	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, parts;
 	float2 force;
 	PairParams k;
 };
@@ -400,18 +400,24 @@ int exchange_halos(SphSim *s) {
 	return SPH_OK;
 }
 
-int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed) {
+enum { GRID_FRONT = 1, GRID_EXCHANGE = 2, GRID_BACK = 4, GRID_ALL = 7 };
+// parts: the strip exchange (NCCL) cannot be captured into a graph, so callers may enqueue the
+// launches before it and after it separately
+int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed, int parts = GRID_ALL) {
 	const GridDesc &g = s->grid;
 	const unsigned nb = blocks_for(s->hostN);
-	CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
-	if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
-	predict_key_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
-	                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
-	if (timed) record_phase(s, PH_PREDICT + 1);
-	if (s->strip.world > 1) {
+	if (parts & GRID_FRONT) {
+		CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
+		if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
+		predict_key_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
+		                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
+		if (timed) record_phase(s, PH_PREDICT + 1);
+	}
+	if ((parts & GRID_EXCHANGE) && s->strip.world > 1) {
 		int rc = exchange_halos(s);
 		if (rc != SPH_OK) return rc;
 	}
+	if (!(parts & GRID_BACK)) return SPH_OK;
 	if (timed) record_phase(s, PH_EXCHANGE + 1);
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
@@ -1109,16 +1115,19 @@ extern "C" int sph_load_scenario(SphHandle s, int idx, int seed) {
 }
 
 // one Update() as a sequence of launches on s->stream (also what a step graph captures)
-static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, float2 force, float invDt) {
+static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, float2 force, float invDt, int parts = GRID_ALL) {
 	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
-	record_phase(s, 0);
-	integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt); // also opens the step
-	s->accFrom = 0xFFFFFFFFu;
-	record_phase(s, PH_INTEGRATE + 1);
-	run_viscosity(s, k, nb);
-	record_phase(s, PH_VISCOSITY + 1);
-	int rc = launch_grid_build(s, dt, true, false, true);
+	if (parts & GRID_FRONT) {
+		record_phase(s, 0);
+		integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt); // also opens the step
+		s->accFrom = 0xFFFFFFFFu;
+		record_phase(s, PH_INTEGRATE + 1);
+		run_viscosity(s, k, nb);
+		record_phase(s, PH_VISCOSITY + 1);
+	}
+	int rc = launch_grid_build(s, dt, true, false, true, parts);
 	if (rc != SPH_OK) return rc;
+	if (!(parts & GRID_BACK)) return SPH_OK;
 	if (exact) launch_density<Exact>(s, k, nb);
 	else launch_density<Fast>(s, k, nb);
 	record_phase(s, PH_DENSITY + 1);
@@ -1169,7 +1178,7 @@ int sph_step(SphHandle s, float dt) {
 	const float invDt = 1.0f / dt; // demo4.cpp:287
 	const float2 force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y); // gravity + externalForce, :306
 
-	// Steady state (nothing appended since the last step, no per-phase timing, one GPU): the ~30
+	// Steady state (nothing appended since the last step, no per-phase timing): the ~27
 	// launches of a step are replayed from a CUDA graph, which removes the launch gaps that dominate
 	// small scenes.  Kernel arguments depend on which half of each double buffer is current, so graphs
 	// are cached per buffer parity, staging capacity, dt, force and parameters.
@@ -1177,11 +1186,12 @@ int sph_step(SphHandle s, float dt) {
 		rc = maybe_resize_halo(s);
 		if (rc != SPH_OK) return rc;
 	}
-	// (strips: NCCL send/recv inside a captured stream dead-locked on this stack (NCCL 2.28.9, driver 580), so
-	// multi-GPU steps are launched kernel by kernel)
-	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2 && s->cfg.world_size == 1;
-	bool replayed = false;
-	if (graphable) {
+	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2;
+	// One GPU: the whole step is one graph.  Strips: NCCL send/recv inside a captured stream dead-locked on
+	// this stack (NCCL 2.28.9, driver 580), so the launches before and after the exchange are two graphs
+	// and the exchange itself is enqueued plainly between them.
+	auto run_part = [&](int parts) -> int {
+		if (!graphable) return enqueue_step(s, dt, k, nb, force, invDt, parts);
 		StepGraphKey key;
 		memset(&key, 0, sizeof(key));
 		key.parity = buffer_parity(s);
@@ -1189,37 +1199,45 @@ int sph_step(SphHandle s, float dt) {
 		key.nb = nb;
 		key.nbodies = (uint32_t)s->bodies.size();
 		key.haloMsgRecords = s->haloMsgRecords;
+		key.parts = (uint32_t)parts;
 		key.force = force;
 		key.k = k;
 		StepGraph *g = nullptr;
 		for (StepGraph &c : s->graphs)
 			if (memcmp(&c.key, &key, sizeof(key)) == 0) g = &c;
 		if (!g) {
-			if (s->graphs.size() >= 8) { // parameters keep changing: drop the oldest
+			if (s->graphs.size() >= 16) { // parameters keep changing: drop the oldest
 				cudaGraphExecDestroy(s->graphs.front().exec);
 				s->graphs.erase(s->graphs.begin());
 			}
 			cudaGraph_t graph = nullptr;
 			CU(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-			rc = enqueue_step(s, dt, k, nb, force, invDt);
+			const int rce = enqueue_step(s, dt, k, nb, force, invDt, parts);
 			const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
-			if (rc != SPH_OK) return rc;
+			if (rce != SPH_OK) return rce;
 			if (ce != cudaSuccess) return fail(s, SPH_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
 			StepGraph made;
 			made.key = key;
 			made.parityAfter = buffer_parity(s);
 			CU(s, cudaGraphInstantiate(&made.exec, graph, 0));
 			cudaGraphDestroy(graph);
-			set_buffer_parity(s, key.parity); // capture only recorded the launches: the state is still "before the step"
+			set_buffer_parity(s, key.parity); // capture only recorded the launches: the state is still "before"
 			s->graphs.push_back(made);
 			g = &s->graphs.back();
 		}
 		CU(s, cudaGraphLaunch(g->exec, s->stream));
 		set_buffer_parity(s, g->parityAfter);
-		replayed = true;
-	}
-	if (!replayed) {
-		rc = enqueue_step(s, dt, k, nb, force, invDt);
+		return SPH_OK;
+	};
+	if (s->cfg.world_size == 1) {
+		rc = run_part(GRID_ALL);
+		if (rc != SPH_OK) return rc;
+	} else {
+		rc = run_part(GRID_FRONT);
+		if (rc != SPH_OK) return rc;
+		rc = enqueue_step(s, dt, k, nb, force, invDt, GRID_EXCHANGE);
+		if (rc != SPH_OK) return rc;
+		rc = run_part(GRID_BACK);
 		if (rc != SPH_OK) return rc;
 	}
 	CU(s, cudaGetLastError());
