@@ -722,6 +722,157 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 	}
 }
 
+// ---- the same sweep with a whole thread block per cell --------------------------------------------
+// One warp per cell leaves most of the GPU idle when a colour has fewer cells than the device has warp
+// slots (the reference's own scenes: 594 cells, 66 per colour), and the chain of a cell's particles is
+// strictly serial.  Here SPH_TEAM_WARPS warps share one cell: the candidate tests and the pair terms of
+// a particle are spread over the warps, the queue is assembled from per-trip ballots with a prefix sum,
+// and warp 0 folds the stored pair terms in queue order - the additions, their order and the lane
+// assignment are exactly those of color_sweep_kernel, so both kernels produce the same bits and the
+// host may pick either by load.
+#define SPH_TEAM_WARPS 8
+__host__ __device__ inline uint32_t team_smem_bytes(uint32_t cap, int pass) {
+	return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) /* sPos (+ sVel) */ + cap * 2u /* queue */ + cap * 8u /* pair terms */ + (cap / 32u + 2u) * 4u /* ballots */;
+}
+
+template <class M, int PASS>
+__global__ void __launch_bounds__(SPH_TEAM_WARPS * 32) color_sweep_team_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
+                                                                               const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
+                                                                               float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
+                                                                               Counters *__restrict__ ctr) {
+	extern __shared__ __align__(16) unsigned char teamSmem[];
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+	float2 *sPos = reinterpret_cast<float2 *>(teamSmem);
+	float2 *sVel = sPos + cap; // viscosity only
+	float2 *sTerm = sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+	uint16_t *queue = reinterpret_cast<uint16_t *>(sTerm + cap);
+	uint32_t *tripMask = reinterpret_cast<uint32_t *>(queue + cap);
+	const uint32_t nList = *colorCount;
+	const int nRows = g.rowHi - g.rowLo;
+	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
+	for (uint32_t idx = blockIdx.x; idx < nList; idx += gridDim.x) {
+		const uint32_t c = colorList[idx];
+		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
+		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
+		uint32_t lo[3], cnt[3];
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			const int y = yl - 1 + r;
+			if (y < 0 || y >= nRows) {
+				lo[r] = 0;
+				cnt[r] = 0;
+			} else {
+				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
+				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
+			}
+		}
+		SweepBlock b;
+		b.lo0 = lo[0];
+		b.lo1 = lo[1];
+		b.lo2 = lo[2];
+		b.off1 = cnt[0];
+		b.off2 = cnt[0] + cnt[1];
+		b.T = b.off2 + cnt[2];
+		b.ownLo = cellStart[c];
+		b.m = cellStart[c + 1] - b.ownLo;
+		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		const uint32_t Tpad = (b.T + 31u) & ~31u, nTrips = Tpad >> 5;
+		if (Tpad > cap) { // too large to stage: warp 0 takes the L2 path of the one-warp kernel (same arithmetic)
+			if (w == 0) {
+				const uint32_t wide = team_smem_bytes(cap, PASS) / 2u;
+				if (b.T <= wide) sweep_cell<M, PASS, false>(k, b, pos, vel, press, sPos, sVel, reinterpret_cast<uint16_t *>(teamSmem), lane, ltMask);
+				else if (lane == 0) atomicOr(&ctr->overflow, 4u);
+			}
+			__syncthreads();
+			continue;
+		}
+		for (uint32_t t = threadIdx.x; t < Tpad; t += SPH_TEAM_WARPS * 32) {
+			if (t < b.T) {
+				const uint32_t j = b.gidx(t);
+				sPos[t] = pos[j];
+				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
+			} else {
+				sPos[t] = make_float2(3.0e18f, 3.0e18f);
+			}
+		}
+		__syncthreads();
+		for (uint32_t kBase = 0; kBase < b.m; kBase += 32) {
+			float2 myPress = make_float2(0.0f, 0.0f);
+			if (PASS == SWEEP_DELTA && kBase + lane < b.m) myPress = press[b.ownLo + kBase + lane];
+			const uint32_t kEnd = min(b.m - kBase, 32u);
+			for (uint32_t kk = 0; kk < kEnd; ++kk) {
+				const uint32_t si = b.ownOff + kBase + kk;
+				const float2 xi = sPos[si];
+				float2 vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
+				if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
+				if (PASS == SWEEP_DELTA) {
+					ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
+					ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
+				}
+				// stage 1a: every warp tests its share of the 32-candidate trips
+				for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
+					const float2 xj = sPos[tr * 32u + lane];
+					const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+					const uint32_t mask = __ballot_sync(0xffffffffu, M::dot2(rx, rx, ry, ry) < k.h2);
+					if (lane == 0) tripMask[tr] = mask;
+				}
+				__syncthreads();
+				// stage 1b: exclusive prefix of the trips' hit counts (every warp redundantly), then the queue in candidate order
+				const uint32_t myMask = lane < nTrips ? tripMask[lane] : 0u; // cap <= 1024: at most 32 trips
+				uint32_t incl = (uint32_t)__popc(myMask);
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+					if ((int)lane >= o) incl += up;
+				}
+				const uint32_t nHit = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t excl = incl - (uint32_t)__popc(myMask);
+				for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
+					const uint32_t mask = __shfl_sync(0xffffffffu, myMask, (int)tr);
+					const uint32_t base = __shfl_sync(0xffffffffu, excl, (int)tr);
+					if (mask & (1u << lane)) queue[base + (uint32_t)__popc(mask & ltMask)] = (uint16_t)(tr * 32u + lane);
+				}
+				__syncthreads();
+				// stage 2: pair terms, partner updated at once; the terms are kept for warp 0
+				for (uint32_t q = w * 32u + lane; q < nHit; q += SPH_TEAM_WARPS * 32) {
+					const uint32_t t = queue[q];
+					bool hit;
+					float2 hlf;
+					if (PASS == SWEEP_DELTA) {
+						const float2 xj = sPos[t];
+						hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+						sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+					} else {
+						const float2 vj = sVel[t];
+						hlf = sweep_viscosity_term<M>(k, xi, vi, sPos[t], vj, hit);
+						if (hit) sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+						else hlf = make_float2(0.0f, 0.0f); // x - (+0) == x bit for bit
+					}
+					sTerm[q] = hlf;
+				}
+				__syncthreads();
+				// the particle's own change: warp 0 repeats the one-warp kernel's additions in its order
+				if (w == 0) {
+					float ax = 0.0f, ay = 0.0f;
+					for (uint32_t q = lane; q < nHit; q += 32) {
+						const float2 hlf = sTerm[q];
+						ax = __fsub_rn(ax, hlf.x);
+						ay = __fsub_rn(ay, hlf.y);
+					}
+					const float2 own = butterfly_sum2_lane0(ax, ay, lane);
+					if (lane == 0) {
+						float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
+						*slot = make_float2(__fadd_rn(own.x, slot->x), __fadd_rn(own.y, slot->y));
+					}
+				}
+				__syncthreads();
+			}
+		}
+		for (uint32_t t = threadIdx.x; t < b.T; t += SPH_TEAM_WARPS * 32) state[b.gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
+		__syncthreads();
+	}
+}
+
 // ---- phases 8+9: body collisions and velocity (demo4.cpp:412-450) ---------------------------------
 // Also closes the step: publishes n = nSorted = nOut for the next one.
 __global__ void __launch_bounds__(SPH_THREADS) collide_velocity_kernel(Counters *__restrict__ ctr, float2 *__restrict__ pos, const float2 *__restrict__ prev,

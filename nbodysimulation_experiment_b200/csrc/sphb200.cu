@@ -457,21 +457,36 @@ template <class M>
 void launch_density(SphSim *s, const PairParams &k, unsigned nb) {
 	density_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->cellOf.in(), s->cellStart, s->dens.in(), s->press.in());
 }
-// nine launches, one per cell colour; in place on pos (delta) or vel (viscosity)
+// nine launches, one per cell colour; in place on pos (delta) or vel (viscosity).  Two kernels with
+// identical results: one warp per cell (large scenes) or one block per cell (scenes whose colours
+// have fewer cells than the GPU has warp slots).
 template <class M, int PASS>
 void launch_sweeps(SphSim *s, const PairParams &k) {
-	const size_t smem = (size_t)SPH_SWEEP_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
 	static bool attrSet = false;
 	if (!attrSet) {
 		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(color_sweep_team_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 		attrSet = true;
 	}
 	// occupied cells of one colour <= min(cells of that colour, particles)
-	uint64_t cells = std::min<uint64_t>(s->listStride, std::max<uint64_t>(s->hostN, 1));
-	unsigned blocks = (unsigned)std::min<uint64_t>((cells + SPH_SWEEP_WARPS - 1) / SPH_SWEEP_WARPS, 148u * 64u);
-	for (int color = 0; color < 9; ++color)
-		color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList + (size_t)color * s->listStride,
-		                                                                             s->colorCount + color, s->pos.in(), s->vel.in(), s->press.in(), s->sweepCap, s->dCtr);
+	const uint64_t cells = std::min<uint64_t>(s->listStride, std::max<uint64_t>(s->hostN, 1));
+	bool team = s->cfg.world_size == 1 && s->hostN < 131072;
+	if (s->cfg.flags & SPH_FLAG_SWEEP_TEAM) team = true;
+	if (s->cfg.flags & SPH_FLAG_SWEEP_WARP) team = false;
+	for (int color = 0; color < 9; ++color) {
+		const uint32_t *list = s->colorList + (size_t)color * s->listStride;
+		if (team) {
+			const uint32_t cap = std::min(s->sweepCap, 1024u);
+			const unsigned blocks = (unsigned)std::min<uint64_t>(cells, 148u * 16u);
+			color_sweep_team_kernel<M, PASS><<<blocks, SPH_TEAM_WARPS * 32, team_smem_bytes(cap, PASS), s->stream>>>(s->grid, k, s->cellStart, list, s->colorCount + color,
+			                                                                                               s->pos.in(), s->vel.in(), s->press.in(), cap, s->dCtr);
+		} else {
+			const size_t smem = (size_t)SPH_SWEEP_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
+			const unsigned blocks = (unsigned)std::min<uint64_t>((cells + SPH_SWEEP_WARPS - 1) / SPH_SWEEP_WARPS, 148u * 64u);
+			color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, list, s->colorCount + color, s->pos.in(), s->vel.in(),
+			                                                                             s->press.in(), s->sweepCap, s->dCtr);
+		}
+	}
 }
 
 int run_viscosity(SphSim *s, const PairParams &k, unsigned nb) {
