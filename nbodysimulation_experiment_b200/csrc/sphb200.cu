@@ -1372,6 +1372,8 @@ int sph_get_stats(SphHandle s, SphStats *out) {
 		out->time_delta_positions = (float)(s->phaseMs[PH_DELTA] * inv);
 		out->time_collisions = (float)(s->phaseMs[PH_COLLIDE] * inv);
 	}
+	if (c.lost)
+		return fail(s, SPH_ERR_STATE, "%u particle-steps left the rows this rank and its two neighbours hold (moved more than the halo in one step)", c.lost);
 	if (c.overflow)
 		return fail(s, SPH_ERR_CAPACITY, "device reported a capacity overflow (flags %u: 1 = particles, 2 = halo buffer, 4 = more candidates in one 3x3 block than the sweep queue holds)",
 		            c.overflow);
