@@ -47,8 +47,9 @@ BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
 # algorithmic HBM bytes per particle of each phase (DESIGN.md "kernels")
 PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "reorder": 44, "density": 16, "delta": 24, "collide_velocity": 32}
-# integrate, 9 x viscosity sweep, predict_key, scan (tiles, sums, add+colour lists), scatter_ids, reorder, density, 9 x delta sweep, collide_velocity
-KERNELS_PER_STEP = {"gs": 27, "gather": 11}
+# integrate, viscosity sweep (1 launch, or 9 with --sweep warp), predict_key, scan (tiles, sums, add+colour lists), scatter_ids, reorder,
+# density, delta sweep (1 or 9), collide_velocity
+KERNELS_PER_STEP = {"gs": 11, "gs9": 27, "gather": 11}
 
 
 def scene_gravity(nx, spacing, scaled):
@@ -133,6 +134,9 @@ def run_ours(args):
 
     from nbodysimulation_experiment_b200 import (SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER,
                                                  ParticleSimulation, pinned_empty, scenes)
+    from nbodysimulation_experiment_b200 import _lib
+
+    sweep_flags = {"auto": 0, "flow": _lib.SPH_FLAG_SWEEP_FLOW, "warp": _lib.SPH_FLAG_SWEEP_WARP, "team": _lib.SPH_FLAG_SWEEP_TEAM}[args.sweep]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -160,7 +164,7 @@ def run_ours(args):
 
     def make(flags=0, which=0):
         build = scenes.bodies_scene if wl.get("bodies") else scenes.block_scene
-        sim = build(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags, relaxation=relaxation, device=local_rank,
+        sim = build(nx, spacing=spacing, gravity=gravity, fp_mode=fp_mode, flags=flags | sweep_flags, relaxation=relaxation, device=local_rank,
                     solver=solver, sweep_capacity=args.sweep_capacity, rank=rank, world_size=world, halo_rows=args.halo_rows)
         if world > 1:
             sim.comm_init(uid[which])
@@ -255,13 +259,17 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         dom = max((k for k in phases if k != "exchange"), key=lambda k: phases[k])
         swept = solver == SPH_SOLVER_COLORED_GS and dom in ("viscosity", "delta")
-        launches = 9 if swept else 1  # a coloured sweep is nine launches, each over the cells of one colour
+        # one launch for all nine colours (color_sweep_flow_kernel) unless --sweep warp/team or a small scene (team kernel)
+        one_launch = args.sweep == "flow" or (args.sweep == "auto" and (world > 1 or n_phase_local >= 131072))
+        launches = 9 if (swept and not one_launch) else 1
+        sweep_kernel = "color_sweep_flow_kernel" if one_launch else ("color_sweep_team_kernel" if args.sweep in ("team", "auto") else "color_sweep_kernel")
         dom_bytes = PHASE_BYTES[dom] * n_phase_local / launches
         launch_ms = phases[dom] / launches
         achieved = dom_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
         step_bytes = BYTES_PER_PARTICLE_STEP * n_total + BYTES_PER_CELL_STEP * cells
         step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
-        kernel_name = {"viscosity": "color_sweep_kernel<Exact, 1>" if swept else "viscosity_kernel<Exact>", "delta": "color_sweep_kernel<Exact, 0>" if swept else "delta_kernel<Exact>",
+        fpn = "Exact" if args.fp == "exact" else "Fast"
+        kernel_name = {"viscosity": f"{sweep_kernel}<{fpn}, 1>" if swept else f"viscosity_kernel<{fpn}>", "delta": f"{sweep_kernel}<{fpn}, 0>" if swept else f"delta_kernel<{fpn}>",
                        "density": "density_kernel<Exact>", "reorder": "reorder_kernel", "predict_key": "predict_key_kernel",
                        "collide_velocity": "collide_velocity_kernel"}.get(dom, dom)
         traffic = None
@@ -269,7 +277,7 @@ def run_ours(args):
         if os.path.exists(tpath) and args.workload == "dambreak_1m" and world == 1 and args.fp == "exact":
             traffic = json.load(open(tpath)).get(kernel_name, {}).get("dram_bytes_per_launch")
         roofline = {
-            "bound": "hbm", "kernel": kernel_name + (" (one of the 9 colour launches of the %s sweep)" % dom if swept else ""),
+            "bound": "hbm", "kernel": kernel_name + ((" (the whole %s sweep, nine colours in one launch)" if one_launch else " (one of the 9 colour launches of the %s sweep)") % dom if swept else ""),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": launch_ms,
             "step_model": {"bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
@@ -285,7 +293,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {nx}x{nx} = {n_total} particles on {world} GPU(s), spacing {spacing}, h = cell = 0.3, dt = 1/60, "
-                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}",
+                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}, sweep {args.sweep}",
                        "particles": n_total, "particles_rank0": n_local, "cells": cells,
                        "candidates_per_particle_rank0": stats.pair_candidates / max(n_local, 1),
                        "l2": "state streamed once per phase (>130 MB/step) and a 256 MiB L2 flush before the timed region",
@@ -293,7 +301,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4" + (" + id" if world > 1 else "") + ") to host memory every step"
                             + ("; double-buffered pinned frames, the copy of frame k overlaps Update k+1" if world == 1 else "")},
-            "gpu_launches": KERNELS_PER_STEP[args.solver] * args.steps,
+            "gpu_launches": KERNELS_PER_STEP["gather" if args.solver == "gather" else ("gs" if (args.sweep == "flow" or (args.sweep == "auto" and (world > 1 or n_local >= 131072))) else "gs9")] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
             "phases_ms": phases,
@@ -405,6 +413,8 @@ def main():
     ap.add_argument("--solver", default="gs", choices=["gs", "gather"], help="coloured Gauss-Seidel sweeps (default) or Jacobi gather")
     ap.add_argument("--relaxation", type=float, default=0.0, help="gather only: omega")
     ap.add_argument("--sweep-capacity", type=int, default=0)
+    ap.add_argument("--sweep", default="auto", choices=["auto", "flow", "warp", "team"],
+                    help="coloured sweep kernel: one launch with dependency flags (flow), nine launches warp-per-cell (warp) or block-per-cell (team)")
     ap.add_argument("--halo-rows", type=int, default=0)
     ap.add_argument("--no-clock-sampler", action="store_true", help="experiment: do not poll NVML during the timed region")
     ap.add_argument("--nx-total", type=int, default=0, help="edge of the whole block, overriding the weak-scaling rule")

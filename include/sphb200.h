@@ -60,7 +60,9 @@ enum {
 	SPH_FLAG_PHASE_TIMING = 1u << 0, /* bracket every phase with CUDA events and fill SphStats.time_* (sph.h:131-141) */
 	SPH_FLAG_NO_GRAPHS = 1u << 1,    /* launch every kernel of a step individually instead of replaying a CUDA graph */
 	SPH_FLAG_SWEEP_TEAM = 1u << 2,   /* coloured sweeps: always one thread block per cell (default: chosen by particle count) */
-	SPH_FLAG_SWEEP_WARP = 1u << 3    /* coloured sweeps: always one warp per cell; both kernels give identical bits */
+	SPH_FLAG_SWEEP_WARP = 1u << 3,   /* coloured sweeps: nine launches, one warp per cell */
+	SPH_FLAG_SWEEP_FLOW = 1u << 4    /* coloured sweeps: one launch for all colours, persistent warps + per-cell dependency flags
+	                                    (default for >= 131072 particles); all three kernels give identical bits */
 };
 
 /* Runtime replacement for the compile-time world of sph.h:18-72. */

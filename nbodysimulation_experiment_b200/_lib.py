@@ -20,6 +20,7 @@ SPH_FLAG_PHASE_TIMING = 1
 SPH_FLAG_NO_GRAPHS = 2
 SPH_FLAG_SWEEP_TEAM = 4
 SPH_FLAG_SWEEP_WARP = 8
+SPH_FLAG_SWEEP_FLOW = 16
 SPH_SOLVER_COLORED_GS = 0
 SPH_SOLVER_GATHER = 1
 SPH_NUM_PHASES = 9

@@ -495,12 +495,14 @@ __global__ void __launch_bounds__(SPH_THREADS) delta_kernel(GridDesc g, PairPara
 
 enum { SWEEP_DELTA = 0, SWEEP_VISCOSITY = 1 };
 
-template <class M>
+// CHECK = false: the caller already knows the pair is within h (stage 1 of the sweeps tested exactly these
+// positions), so the range test of sph.h:488 is not repeated.
+template <class M, bool CHECK = true>
 __device__ __forceinline__ float2 sweep_delta_term(const PairParams &k, float2 xi, float2 ppi, float2 xj, bool &hit) {
 	// SPHComputeDelta, sph.h:483-495, then * 0.5f (demo4.cpp:250-251)
 	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
 	float r2 = M::dot2(rx, rx, ry, ry);
-	hit = r2 < k.h2;
+	hit = CHECK ? (r2 < k.h2) : true;
 	if (!hit) return make_float2(0.0f, 0.0f);
 	float r, inv;
 	M::len_inv(r2, r, inv);
@@ -509,13 +511,13 @@ __device__ __forceinline__ float2 sweep_delta_term(const PairParams &k, float2 x
 	return make_float2(M::mul(M::mul(d, M::mul(rx, inv)), 0.5f), M::mul(M::mul(d, M::mul(ry, inv)), 0.5f));
 }
 
-template <class M>
+template <class M, bool CHECK = true>
 __device__ __forceinline__ float2 sweep_viscosity_term(const PairParams &k, float2 xi, float2 vi, float2 xj, float2 vj, bool &hit) {
 	// SPHComputeViscosityForce, sph.h:497-512, then * 0.5f * deltaTime (demo4.cpp:233-234)
 	hit = false;
 	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
 	float r2 = M::dot2(rx, rx, ry, ry);
-	if (!(r2 < k.h2)) return make_float2(0.0f, 0.0f);
+	if (CHECK && !(r2 < k.h2)) return make_float2(0.0f, 0.0f);
 	float r, inv;
 	M::len_inv(r2, r, inv);
 	float q = M::mul(r, k.invH);
@@ -568,7 +570,9 @@ struct SweepBlock {
 	__device__ __forceinline__ uint32_t gidx(uint32_t t) const { return t < off1 ? lo0 + t : (t < off2 ? lo1 + (t - off1) : lo2 + (t - off2)); }
 };
 
-template <class M, int PASS, bool STAGED>
+// COHERENT: the staging loads bypass L1 (ld.global.cg) because another SM may have rewritten the
+// block earlier in the SAME launch (color_sweep_flow_kernel); the per-colour kernels read through L1.
+template <class M, int PASS, bool STAGED, bool COHERENT = false>
 __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock &b, float2 *pos, float2 *vel, const float2 *__restrict__ press,
                                            float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask) {
 	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
@@ -577,8 +581,8 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 		for (uint32_t t = lane; t < Tpad; t += 32) {
 			if (t < b.T) {
 				const uint32_t j = b.gidx(t);
-				sPos[t] = pos[j];
-				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
+				sPos[t] = COHERENT ? __ldcg(&pos[j]) : pos[j];
+				if (PASS == SWEEP_VISCOSITY) sVel[t] = COHERENT ? __ldcg(&vel[j]) : vel[j];
 			} else {
 				sPos[t] = make_float2(3.0e18f, 3.0e18f); // never within h of anything
 			}
@@ -626,7 +630,7 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 				if (PASS == SWEEP_DELTA) {
 					float2 *slot = STAGED ? &sPos[t] : &pos[b.gidx(t)];
 					const float2 xj = STAGED ? *slot : __ldcg(slot);
-					const float2 hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+					const float2 hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit); // queued = within h, nothing moved it since stage 1
 					const float2 moved = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
 					if (STAGED) *slot = moved;
 					else __stcg(slot, moved);
@@ -637,7 +641,7 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 					float2 *slot = STAGED ? &sVel[t] : &vel[j];
 					const float2 vj = STAGED ? *slot : __ldcg(slot);
 					const float2 xj = STAGED ? sPos[t] : __ldcg(&pos[j]);
-					const float2 hlf = sweep_viscosity_term<M>(k, xi, vi, xj, vj, hit);
+					const float2 hlf = sweep_viscosity_term<M, false>(k, xi, vi, xj, vj, hit);
 					if (hit) {
 						const float2 moved = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
 						if (STAGED) *slot = moved;
@@ -719,6 +723,120 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
 			atomicOr(&ctr->overflow, 4u);
 		}
+	}
+}
+
+// ---- the nine colours in ONE launch: dependency-driven sweep --------------------------------------
+// Nine launches per pass leave eighteen tails per step in which most of the GPU waits for the last
+// few cells of a colour.  Here the occupied cells of all colours form one queue (colour 0's list,
+// then colour 1's, ...) that persistent warps drain through an atomic ticket.  A cell of colour c may
+// start once every occupied cell of a LOWER colour whose 3x3 footprint overlaps its own - the cells
+// within two rows/columns - has finished; cells of a higher colour inside that range wait for it by
+// the same rule.  Cells that are further apart never touch the same particles.  Every cell therefore
+// reads exactly the state it reads in the nine-launch version and the results are bit-identical.
+// Deadlock-free: tickets are handed out in queue order and a warp works its tickets in order, so the
+// unfinished cell with the lowest ticket only waits for finished ones and its warp is running it.
+// `flow[0]` is the ticket counter and `flow[1 + cell]` the done flag; the host zeroes both before
+// the launch.  Loads of particle state bypass L1 (another SM may have just rewritten it).
+#define SPH_FLOW_WARPS 4
+#define SPH_FLOW_MIN_BLOCKS 12 // 48 warps per SM: the sweep is issue-latency bound, more warps hide more of it
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <class M, int PASS>
+__global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
+    color_sweep_flow_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ colorList, uint32_t listStride,
+                            const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
+                            Counters *__restrict__ ctr, uint32_t *flow) {
+	extern __shared__ __align__(16) unsigned char sweepSmem[];
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+	unsigned char *mine = sweepSmem + (size_t)w * sweep_bytes_per_warp(cap, PASS);
+	float2 *sPos = reinterpret_cast<float2 *>(mine);
+	float2 *sVel = sPos + cap; // viscosity only
+	uint16_t *queueStaged = reinterpret_cast<uint16_t *>(sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1));
+	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
+	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
+	const int nRows = g.rowHi - g.rowLo;
+	// queue position of each colour's first cell
+	uint32_t first[10];
+	first[0] = 0;
+#pragma unroll
+	for (int c = 0; c < 9; ++c) first[c + 1] = first[c] + colorCount[c];
+	const uint32_t total = first[9];
+	uint32_t ticket = 0;
+	if (lane == 0) ticket = atomicAdd(&flow[0], 1u);
+	ticket = __shfl_sync(0xffffffffu, ticket, 0);
+	while (ticket < total) {
+		uint32_t nextTicket = 0;
+		if (lane == 0) nextTicket = atomicAdd(&flow[0], 1u); // drawn now, needed after this cell: the round trip is hidden
+		int color = 0;
+		uint32_t colorFirst = 0;
+#pragma unroll
+		for (int cc = 1; cc < 9; ++cc)
+			if (ticket >= first[cc]) {
+				color = cc;
+				colorFirst = first[cc];
+			}
+		const uint32_t c = colorList[(size_t)color * listStride + (ticket - colorFirst)];
+		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
+		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
+		uint32_t lo[3], cnt[3];
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			const int y = yl - 1 + r;
+			if (y < 0 || y >= nRows) {
+				lo[r] = 0;
+				cnt[r] = 0;
+			} else {
+				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
+				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
+			}
+		}
+		SweepBlock b;
+		b.lo0 = lo[0];
+		b.lo1 = lo[1];
+		b.lo2 = lo[2];
+		b.off1 = cnt[0];
+		b.off2 = cnt[0] + cnt[1];
+		b.T = b.off2 + cnt[2];
+		b.ownLo = cellStart[c];
+		b.m = cellStart[c + 1] - b.ownLo;
+		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		// wait for the occupied lower-colour cells of the 5x5 neighbourhood: lane l looks after cell (l%5-2, l/5-2)
+		{
+			const uint32_t *flag = nullptr;
+			if (lane < 25u && lane != 12u) {
+				const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
+				if (nx >= 0 && nx < g.gx && ny >= 0 && ny < nRows) {
+					const int ncolor = (int)(((uint32_t)(ny + g.rowLo) % 3u) * 3u + (uint32_t)nx % 3u);
+					const uint32_t nc = (uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx;
+					if (ncolor < color && cellStart[nc + 1u] > cellStart[nc]) flag = flow + 1 + nc;
+				}
+			}
+			for (;;) {
+				if (flag && ld_acquire_gpu(flag) != 0u) flag = nullptr;
+				if (__all_sync(0xffffffffu, flag == nullptr)) break;
+				__nanosleep(200);
+			}
+			__syncwarp();
+		}
+		if (((b.T + 31u) & ~31u) <= cap) {
+			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask);
+		} else if (b.T <= wideCap) {
+			sweep_cell<M, PASS, false, true>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask);
+		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
+			atomicOr(&ctr->overflow, 4u);
+		}
+		// publish: every lane's stores are ordered before the flag
+		__threadfence();
+		__syncwarp();
+		if (lane == 0) st_release_gpu(flow + 1 + c, 1u);
+		ticket = __shfl_sync(0xffffffffu, nextTicket, 0);
 	}
 }
 
@@ -840,11 +958,11 @@ __global__ void __launch_bounds__(SPH_TEAM_WARPS * 32) color_sweep_team_kernel(G
 					float2 hlf;
 					if (PASS == SWEEP_DELTA) {
 						const float2 xj = sPos[t];
-						hlf = sweep_delta_term<M>(k, xi, ppi, xj, hit);
+						hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit);
 						sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
 					} else {
 						const float2 vj = sVel[t];
-						hlf = sweep_viscosity_term<M>(k, xi, vi, sPos[t], vj, hit);
+						hlf = sweep_viscosity_term<M, false>(k, xi, vi, sPos[t], vj, hit);
 						if (hit) sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
 						else hlf = make_float2(0.0f, 0.0f); // x - (+0) == x bit for bit
 					}

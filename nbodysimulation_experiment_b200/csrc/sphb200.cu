@@ -127,6 +127,7 @@ struct SphSim {
 	uint32_t nTiles = 0;
 	// occupied cells per colour for the coloured Gauss-Seidel sweeps
 	uint32_t *colorCount = nullptr, *colorList = nullptr;
+	uint32_t *sweepFlow = nullptr; // [0] ticket counter, [1 + cell] done flag of the one-launch sweep (color_sweep_flow_kernel)
 	uint32_t listStride = 0, sweepCap = 512;
 	bool sweepAdaptive = true;       // pick the staging capacity from the candidate-list maximum of recent steps
 	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
@@ -457,22 +458,51 @@ template <class M>
 void launch_density(SphSim *s, const PairParams &k, unsigned nb) {
 	density_kernel<M><<<nb, SPH_THREADS, 0, s->stream>>>(s->grid, k, s->dCtr, s->pos.in(), s->cellOf.in(), s->cellStart, s->dens.in(), s->press.in());
 }
-// nine launches, one per cell colour; in place on pos (delta) or vel (viscosity).  Two kernels with
-// identical results: one warp per cell (large scenes) or one block per cell (scenes whose colours
-// have fewer cells than the GPU has warp slots).
+// In place on pos (delta) or vel (viscosity).  Three kernels with identical results:
+//   * color_sweep_flow_kernel - one launch for all nine colours, persistent warps, per-cell dependency flags (large scenes);
+//   * color_sweep_kernel      - nine launches, one warp per cell (SPH_FLAG_SWEEP_WARP);
+//   * color_sweep_team_kernel - nine launches, one block per cell, for scenes whose colours have fewer cells than the
+//                               GPU has warp slots (the reference's own scenes).
 template <class M, int PASS>
 void launch_sweeps(SphSim *s, const PairParams &k) {
 	static bool attrSet = false;
+	static int numSMs = 148;
+	static int flowBlocksPerSM[97] = {};
 	if (!attrSet) {
 		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		cudaFuncSetAttribute(color_sweep_team_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+		// resident blocks per SM of the persistent kernel for every staging capacity (32..3072 in steps of 32), asked
+		// once here: the first steps of a simulation are never inside a graph capture
+		for (uint32_t c32 = 1; c32 <= 96; ++c32) {
+			int nbk = 0;
+			const size_t bytes = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(c32 * 32u, PASS);
+			if (bytes <= 200u * 1024u) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, color_sweep_flow_kernel<M, PASS>, SPH_FLOW_WARPS * 32, bytes);
+			flowBlocksPerSM[c32] = nbk;
+		}
+		cudaGetLastError();
 		attrSet = true;
 	}
 	// occupied cells of one colour <= min(cells of that colour, particles)
 	const uint64_t cells = std::min<uint64_t>(s->listStride, std::max<uint64_t>(s->hostN, 1));
 	bool team = s->cfg.world_size == 1 && s->hostN < 131072;
 	if (s->cfg.flags & SPH_FLAG_SWEEP_TEAM) team = true;
-	if (s->cfg.flags & SPH_FLAG_SWEEP_WARP) team = false;
+	if (s->cfg.flags & (SPH_FLAG_SWEEP_WARP | SPH_FLAG_SWEEP_FLOW)) team = false;
+	const bool flow = !team && !(s->cfg.flags & SPH_FLAG_SWEEP_WARP);
+	if (flow) {
+		// persistent: as many blocks as are resident at once (more would only draw a ticket and leave)
+		const size_t smem = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
+		const int occBlocks = std::max(1, flowBlocksPerSM[std::min(96u, (s->sweepCap + 31u) / 32u)]);
+		const uint64_t want = (9 * cells + SPH_FLOW_WARPS - 1) / SPH_FLOW_WARPS;
+		const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
+		cudaMemsetAsync(s->sweepFlow, 0, ((size_t)s->grid.nCells + 1) * sizeof(uint32_t), s->stream);
+		color_sweep_flow_kernel<M, PASS><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
+		                                                                                 s->vel.in(), s->press.in(), s->sweepCap, s->dCtr, s->sweepFlow);
+		return;
+	}
 	for (int color = 0; color < 9; ++color) {
 		const uint32_t *list = s->colorList + (size_t)color * s->listStride;
 		if (team) {
@@ -526,7 +556,8 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	cudaFree(s->cellStart);
 	cudaFree(s->tileSums);
 	cudaFree(s->colorList);
-	s->cellCount = s->cellStart = s->tileSums = s->colorList = nullptr;
+	cudaFree(s->sweepFlow);
+	s->cellCount = s->cellStart = s->tileSums = s->colorList = s->sweepFlow = nullptr;
 	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
 	CU(s, cudaMalloc(&s->cellCount, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
 	CU(s, cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
@@ -534,6 +565,7 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	CU(s, cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
 	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
 	return SPH_OK;
 }
 
@@ -752,6 +784,7 @@ int sph_destroy(SphHandle s) {
 	cudaFree(s->tileSums);
 	cudaFree(s->colorCount);
 	cudaFree(s->colorList);
+	cudaFree(s->sweepFlow);
 	cudaFree(s->dBodies);
 	cudaFree(s->dRecords);
 	cudaFree(s->dRenderPos);

@@ -313,11 +313,12 @@ def test_million_particle_invariants(pkg):
 
 
 # ---- the coloured Gauss-Seidel sweeps -------------------------------------------------------------
-@pytest.mark.parametrize("cap", [96, 160, 512])
-def test_colored_sweep_staging_capacity_does_not_change_results(pkg, cap):
+@pytest.mark.parametrize("cap,flags", [(96, 0), (160, 0), (512, 0), (96, 16), (160, 8), (512, 16)])
+def test_colored_sweep_staging_capacity_does_not_change_results(pkg, cap, flags):
     """Blocks that do not fit the shared-memory staging take the L2 path: same bits either way.
-    Scene 0 has 250-360 candidates per block, so cap=96/160 forces the L2 path everywhere."""
-    gpu = pkg.ParticleSimulation(sweep_capacity=cap)
+    Scene 0 has 250-360 candidates per block, so cap=96/160 forces the L2 path everywhere.
+    flags: 0 = block per cell (default for small scenes), 8 = nine launches warp per cell, 16 = one-launch flow kernel."""
+    gpu = pkg.ParticleSimulation(sweep_capacity=cap, flags=flags)
     gpu.LoadScenario(0, seed=1)
     cpu = CpuSim("oracle", mode=MODE_COLORED)
     cpu.load_scenario(0, 1)
@@ -329,11 +330,14 @@ def test_colored_sweep_staging_capacity_does_not_change_results(pkg, cap):
     cpu.close()
 
 
-def test_colored_block_bitwise_vs_oracle(pkg):
-    """16 384 particles from the device-side generator, dense regime (spacing h/6), 12 steps."""
+@pytest.mark.parametrize("sweep", ["team", "warp", "flow"])
+def test_colored_block_bitwise_vs_oracle(pkg, sweep):
+    """16 384 particles from the device-side generator, dense regime (spacing h/6), 12 steps, each of the
+    three sweep kernels."""
     from nbodysimulation_experiment_b200 import scenes
 
-    gpu = scenes.fill_block(scenes.block_scene(128, spacing=0.05, gravity=(0.0, -8.3)))
+    flags = {"team": pkg._lib.SPH_FLAG_SWEEP_TEAM, "warp": pkg._lib.SPH_FLAG_SWEEP_WARP, "flow": pkg._lib.SPH_FLAG_SWEEP_FLOW}[sweep]
+    gpu = scenes.fill_block(scenes.block_scene(128, spacing=0.05, gravity=(0.0, -8.3), flags=flags))
     n = gpu.GetParticleCount()
     assert n == 128 * 128
     init = gpu.particles()
@@ -466,7 +470,8 @@ def test_block_per_cell_and_warp_per_cell_sweeps_agree_with_the_oracle(pkg, scen
     cpu.load_scenario(scene, 6)
     cpu.advance(DT, steps)
     want = cpu.particles()
-    for flags in (pkg._lib.SPH_FLAG_SWEEP_TEAM, pkg._lib.SPH_FLAG_SWEEP_WARP):
+    for flags in (pkg._lib.SPH_FLAG_SWEEP_TEAM, pkg._lib.SPH_FLAG_SWEEP_WARP, pkg._lib.SPH_FLAG_SWEEP_FLOW,
+                  pkg._lib.SPH_FLAG_SWEEP_FLOW | pkg._lib.SPH_FLAG_NO_GRAPHS):
         s = pkg.ParticleSimulation(flags=flags)
         s.LoadScenario(scene, seed=6)
         for _ in range(steps):
@@ -474,6 +479,28 @@ def test_block_per_cell_and_warp_per_cell_sweeps_agree_with_the_oracle(pkg, scen
         assert_bits_equal(s.particles(), want, f"scene {scene}, sweep flags {flags}")
         s.close()
     cpu.close()
+
+
+@pytest.mark.parametrize("nx,spacing,g,steps", [(512, 0.1, -10.0, 60), (1024, 0.1, -0.5219, 24), (384, 0.05, -3.0, 16)])
+def test_one_launch_flow_sweep_equals_nine_launch_sweep_at_scale(pkg, nx, spacing, g, steps):
+    """The dependency-driven one-launch sweep (persistent warps, per-cell done flags) against the nine
+    per-colour launches at sizes where every SM is busy and cells of different colours really run
+    concurrently: 262 144 particles in a violent collapse (g = -10), the 1M bench scene, a dense block.
+    Bit-identical state, and two flow runs agree with each other (no ordering left to chance)."""
+    from nbodysimulation_experiment_b200 import scenes
+
+    runs = []
+    for flags in (pkg._lib.SPH_FLAG_SWEEP_WARP, pkg._lib.SPH_FLAG_SWEEP_FLOW, pkg._lib.SPH_FLAG_SWEEP_FLOW | pkg._lib.SPH_FLAG_NO_GRAPHS):
+        sim = scenes.fill_block(scenes.block_scene(nx, spacing=spacing, gravity=(0.0, g), flags=flags))
+        assert sim.GetParticleCount() == nx * nx
+        for _ in range(steps):
+            sim.Update(DT)
+        runs.append(sim.particles())
+        sim.GetStats()  # raises on a capacity / overflow flag
+        sim.close()
+    assert np.isfinite(runs[0]).all()
+    assert_bits_equal(runs[1], runs[0], f"flow vs nine launches, {nx}x{nx}")
+    assert_bits_equal(runs[2], runs[0], f"flow (plain launches) vs nine launches, {nx}x{nx}")
 
 
 def test_graph_replay_is_bit_identical_to_plain_launches(pkg):
