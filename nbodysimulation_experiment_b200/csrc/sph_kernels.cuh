@@ -347,30 +347,65 @@ __global__ void __launch_bounds__(SPH_THREADS) scan_add_kernel(uint32_t *__restr
 		if (first + k < nCells) cellStart[first + k] += off;
 }
 
-// scan_add_kernel and color_lists_kernel in one pass over the cells (coloured solver): the tile offset
-// is added, and occupied cells are filed under their colour.  A cell's count is start[c+1]-start[c];
-// the next cell may belong to the next tile, whose offset is added here by hand.
-__global__ void __launch_bounds__(SPH_THREADS) scan_add_lists_kernel(GridDesc g, uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ tileSums,
-                                                                    const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ colorCount,
-                                                                    uint32_t *__restrict__ colorList, uint32_t listStride) {
-	const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; // blockDim divides SPH_SCAN_TILE: one tile offset per block
-	int color = -1;
-	if (c < g.nCells) {
-		cellStart[c] += tileSums[c / SPH_SCAN_TILE];
-		if (cellCount[c] > 0) {
-			const uint32_t yl = c / (uint32_t)g.gx, cx = c - yl * (uint32_t)g.gx;
-			color = (int)(((yl + (uint32_t)g.rowLo) % 3u) * 3u + cx % 3u);
-		}
-	}
+// ---- colour lists in row-major order ---------------------------------------------------------------
+// The one-launch sweep (color_sweep_flow_kernel) hands cells out in list order and a cell waits for its
+// lower-colour neighbours; if a colour's list walks the grid front to back, the cells a newcomer depends on
+// were handed out a whole colour earlier and nobody ever waits.  Lists appended with atomics are shuffled over
+// a quarter of the domain, so these three kernels build them sorted instead: one warp per (grid row, cx mod 3)
+// counts its occupied cells, one block turns the counts into list offsets (rows of equal colour in ascending
+// order), and the same warps write the cells behind their offset.  Deterministic as a side effect.
+#define SPH_ROWLIST_WARPS 6 // two rows (x three column classes) per block
+
+__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ rowColor) {
+	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
+	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
+	if (wid >= nRows * 3u) return;
+	const uint32_t row = wid / 3u, a = wid - row * 3u;
+	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
+	uint32_t n = 0;
+	for (uint32_t cx = a + 3u * lane; cx < (uint32_t)g.gx; cx += 96u) n += cc[cx] ? 1u : 0u;
+	n = warp_sum(n);
+	if (lane == 0) rowColor[wid] = n;
+}
+
+// nine warps, one per colour k = (row mod 3)*3 + a: exclusive scan of rowColor over that colour's rows, in place
+__global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount) {
+	const uint32_t k = threadIdx.x >> 5, lane = lane_id();
+	const uint32_t b = k / 3u, a = k - b * 3u;
+	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
+	const uint32_t r0 = (b + 3u - (uint32_t)g.rowLo % 3u) % 3u; // first local row whose global row is b mod 3
+	uint32_t running = 0;
+	for (uint32_t base = r0; base < nRows; base += 96u) {
+		const uint32_t row = base + 3u * lane;
+		const uint32_t v = row < nRows ? rowColor[row * 3u + a] : 0u;
+		uint32_t inc = v;
 #pragma unroll
-	for (int k = 0; k < 9; ++k) {
-		const uint32_t mask = __ballot_sync(0xffffffffu, color == k);
-		if (!mask) continue;
-		const int leader = __ffs(mask) - 1;
-		uint32_t at = 0;
-		if ((int)lane_id() == leader) at = atomicAdd(&colorCount[k], (uint32_t)__popc(mask));
-		at = __shfl_sync(0xffffffffu, at, leader);
-		if (color == k) colorList[(uint32_t)k * listStride + at + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u))] = c;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+			if ((int)lane >= o) inc += up;
+		}
+		if (row < nRows) rowColor[row * 3u + a] = running + inc - v;
+		running += __shfl_sync(0xffffffffu, inc, 31);
+	}
+	if (lane == 0) colorCount[k] = running;
+}
+
+__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, const uint32_t *__restrict__ rowColor,
+                                                                               uint32_t *__restrict__ colorList, uint32_t listStride) {
+	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
+	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
+	if (wid >= nRows * 3u) return;
+	const uint32_t row = wid / 3u, a = wid - row * 3u;
+	const uint32_t k = ((row + (uint32_t)g.rowLo) % 3u) * 3u + a;
+	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
+	uint32_t *list = colorList + (size_t)k * listStride;
+	uint32_t at = rowColor[wid];
+	for (uint32_t c0 = a; c0 < (uint32_t)g.gx; c0 += 96u) { // warp-uniform trip count
+		const uint32_t cx = c0 + 3u * lane;
+		const bool occ = cx < (uint32_t)g.gx && cc[cx] != 0u;
+		const uint32_t mask = __ballot_sync(0xffffffffu, occ);
+		if (occ) list[at + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = row * (uint32_t)g.gx + cx;
+		at += (uint32_t)__popc(mask);
 	}
 }
 
@@ -739,7 +774,7 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 // `flow[0]` is the ticket counter and `flow[1 + cell]` the done flag; the host zeroes both before
 // the launch.  Loads of particle state bypass L1 (another SM may have just rewritten it).
 #define SPH_FLOW_WARPS 4
-#define SPH_FLOW_MIN_BLOCKS 12 // 48 warps per SM: the sweep is issue-latency bound, more warps hide more of it
+#define SPH_FLOW_MIN_BLOCKS 10 // 48 registers: at 40 (12 blocks) ptxas rematerialises addresses inside the pair loops, +26 % instructions (ncu, r1b)
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 	uint32_t v;
@@ -762,26 +797,25 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
 	const int nRows = g.rowHi - g.rowLo;
-	// queue position of each colour's first cell
-	uint32_t first[10];
-	first[0] = 0;
-#pragma unroll
-	for (int c = 0; c < 9; ++c) first[c + 1] = first[c] + colorCount[c];
-	const uint32_t total = first[9];
 	uint32_t ticket = 0;
 	if (lane == 0) ticket = atomicAdd(&flow[0], 1u);
 	ticket = __shfl_sync(0xffffffffu, ticket, 0);
-	while (ticket < total) {
+	for (;;) {
+		// which colour's list the ticket falls into (nine counts, re-read per cell: they would cost nine registers to keep)
+		int color = -1;
+		uint32_t colorFirst = 0, seen = 0;
+#pragma unroll
+		for (int cc = 0; cc < 9; ++cc) {
+			const uint32_t n = __ldg(&colorCount[cc]);
+			if (ticket >= seen && ticket < seen + n) {
+				color = cc;
+				colorFirst = seen;
+			}
+			seen += n;
+		}
+		if (color < 0) break; // ticket >= total: the queue is empty
 		uint32_t nextTicket = 0;
 		if (lane == 0) nextTicket = atomicAdd(&flow[0], 1u); // drawn now, needed after this cell: the round trip is hidden
-		int color = 0;
-		uint32_t colorFirst = 0;
-#pragma unroll
-		for (int cc = 1; cc < 9; ++cc)
-			if (ticket >= first[cc]) {
-				color = cc;
-				colorFirst = first[cc];
-			}
 		const uint32_t c = colorList[(size_t)color * listStride + (ticket - colorFirst)];
 		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
 		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
@@ -832,8 +866,8 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
 			atomicOr(&ctr->overflow, 4u);
 		}
-		// publish: every lane's stores are ordered before the flag
-		__threadfence();
+		// publish: every lane fences its own stores, the warp joins, then one lane raises the flag
+		asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		__syncwarp();
 		if (lane == 0) st_release_gpu(flow + 1 + c, 1u);
 		ticket = __shfl_sync(0xffffffffu, nextTicket, 0);

@@ -127,6 +127,7 @@ struct SphSim {
 	uint32_t nTiles = 0;
 	// occupied cells per colour for the coloured Gauss-Seidel sweeps
 	uint32_t *colorCount = nullptr, *colorList = nullptr;
+	uint32_t *rowColor = nullptr;  // occupied cells per (local row, cx mod 3), then their offsets in the colour lists
 	uint32_t *sweepFlow = nullptr; // [0] ticket counter, [1 + cell] done flag of the one-launch sweep (color_sweep_flow_kernel)
 	uint32_t listStride = 0, sweepCap = 512;
 	bool sweepAdaptive = true;       // pick the staging capacity from the candidate-list maximum of recent steps
@@ -422,12 +423,12 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	if (timed) record_phase(s, PH_EXCHANGE + 1);
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
-	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) {
-		cudaMemsetAsync(s->colorCount, 0, 9 * sizeof(uint32_t), s->stream);
-		scan_add_lists_kernel<<<(g.nCells + SPH_THREADS - 1) / SPH_THREADS, SPH_THREADS, 0, s->stream>>>(g, s->cellStart, s->tileSums, s->cellCount, s->colorCount,
-		                                                                                           s->colorList, s->listStride);
-	} else {
-		scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
+	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
+	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) { // occupied cells per colour, each list in row-major order
+		const unsigned rowWarps = (unsigned)(g.rowHi - g.rowLo) * 3u, rowBlocks = (rowWarps + SPH_ROWLIST_WARPS - 1) / SPH_ROWLIST_WARPS;
+		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor);
+		color_rows_scan_kernel<<<1, 9 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount);
+		color_rows_fill_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->colorList, s->listStride);
 	}
 	if (timed) record_phase(s, PH_SCAN + 1);
 	scatter_ids_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->cellNew, s->rank, s->id.in(), s->cellStart, s->slotId);
@@ -557,7 +558,8 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	cudaFree(s->tileSums);
 	cudaFree(s->colorList);
 	cudaFree(s->sweepFlow);
-	s->cellCount = s->cellStart = s->tileSums = s->colorList = s->sweepFlow = nullptr;
+	cudaFree(s->rowColor);
+	s->cellCount = s->cellStart = s->tileSums = s->colorList = s->sweepFlow = s->rowColor = nullptr;
 	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
 	CU(s, cudaMalloc(&s->cellCount, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
 	CU(s, cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
@@ -566,6 +568,7 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
 	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->rowColor, (size_t)(g.rowHi - g.rowLo) * 3 * sizeof(uint32_t)));
 	return SPH_OK;
 }
 
@@ -785,6 +788,7 @@ int sph_destroy(SphHandle s) {
 	cudaFree(s->colorCount);
 	cudaFree(s->colorList);
 	cudaFree(s->sweepFlow);
+	cudaFree(s->rowColor);
 	cudaFree(s->dBodies);
 	cudaFree(s->dRecords);
 	cudaFree(s->dRenderPos);
