@@ -613,13 +613,40 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
 	const uint32_t Tpad = (b.T + 31u) & ~31u;
 	if (STAGED) {
-		for (uint32_t t = lane; t < Tpad; t += 32) {
-			if (t < b.T) {
-				const uint32_t j = b.gidx(t);
-				sPos[t] = COHERENT ? __ldcg(&pos[j]) : pos[j];
-				if (PASS == SWEEP_VISCOSITY) sVel[t] = COHERENT ? __ldcg(&vel[j]) : vel[j];
-			} else {
-				sPos[t] = make_float2(3.0e18f, 3.0e18f); // never within h of anything
+		if (COHERENT) {
+			// four trips of loads in flight before the first one is consumed: the block comes from L2 (~1 us away
+			// under load) and a warp has nothing else to do until it is staged
+			for (uint32_t t0 = lane; t0 < Tpad; t0 += 128) {
+				float2 p[4], v[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t t = t0 + 32u * (uint32_t)u;
+					p[u] = make_float2(3.0e18f, 3.0e18f); // never within h of anything
+					v[u] = make_float2(0.0f, 0.0f);
+					if (t < b.T) {
+						const uint32_t j = b.gidx(t);
+						p[u] = __ldcg(&pos[j]);
+						if (PASS == SWEEP_VISCOSITY) v[u] = __ldcg(&vel[j]);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					const uint32_t t = t0 + 32u * (uint32_t)u;
+					if (t < Tpad) {
+						sPos[t] = p[u];
+						if (PASS == SWEEP_VISCOSITY) sVel[t] = v[u];
+					}
+				}
+			}
+		} else {
+			for (uint32_t t = lane; t < Tpad; t += 32) {
+				if (t < b.T) {
+					const uint32_t j = b.gidx(t);
+					sPos[t] = pos[j];
+					if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
+				} else {
+					sPos[t] = make_float2(3.0e18f, 3.0e18f); // never within h of anything
+				}
 			}
 		}
 		__syncwarp();
@@ -797,26 +824,38 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
 	const int nRows = g.rowHi - g.rowLo;
-	uint32_t ticket = 0;
-	if (lane == 0) ticket = atomicAdd(&flow[0], 1u);
-	ticket = __shfl_sync(0xffffffffu, ticket, 0);
-	for (;;) {
-		// which colour's list the ticket falls into (nine counts, re-read per cell: they would cost nine registers to keep)
-		int color = -1;
-		uint32_t colorFirst = 0, seen = 0;
+	// Tickets are drawn two cells ahead and the cell behind the next ticket is looked up one cell ahead, so that
+	// neither the atomic's round trip nor the list lookup sits on a cell's critical path.  Lane 1 increments a per-warp decoy
+	// word alongside on purpose: on an address it can prove uniform, ptxas warp-aggregates the atomic (atom.inc and
+	// run-time increments too) and broadcasts, i.e. waits for, its result on the spot.
+	__shared__ uint32_t counts[9]; // cells per colour: shared memory, nine registers per thread would cost occupancy
+	if (threadIdx.x < 9) counts[threadIdx.x] = colorCount[threadIdx.x];
+	const uint32_t decoy = 1u + g.nCells + (blockIdx.x * SPH_FLOW_WARPS + w); // one word per warp behind the flags
+	__syncthreads();
+	auto draw_ticket = [&]() -> uint32_t {
+		uint32_t t = 0;
+		if (lane < 2u) asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(flow + (lane == 0u ? 0u : decoy)) : "memory");
+		return t; // valid in lane 0
+	};
+	// queue position -> cell (SPH_KEY_NONE past the end); the colour is recomputed from the cell where needed
+	auto cell_of_ticket = [&](uint32_t t) -> uint32_t {
+		uint32_t seen = 0, at = 0xffffffffu, base = 0;
 #pragma unroll
 		for (int cc = 0; cc < 9; ++cc) {
-			const uint32_t n = __ldg(&colorCount[cc]);
-			if (ticket >= seen && ticket < seen + n) {
-				color = cc;
-				colorFirst = seen;
+			if (t >= seen && t < seen + counts[cc]) {
+				at = t - seen;
+				base = (uint32_t)cc * listStride;
 			}
-			seen += n;
+			seen += counts[cc];
 		}
-		if (color < 0) break; // ticket >= total: the queue is empty
-		uint32_t nextTicket = 0;
-		if (lane == 0) nextTicket = atomicAdd(&flow[0], 1u); // drawn now, needed after this cell: the round trip is hidden
-		const uint32_t c = colorList[(size_t)color * listStride + (ticket - colorFirst)];
+		return at == 0xffffffffu ? SPH_KEY_NONE : __ldg(&colorList[(size_t)base + at]);
+	};
+	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0));
+	uint32_t ticketAfter = draw_ticket(); // lane 0; consumed one iteration later
+	uint32_t published = SPH_KEY_NONE;    // the cell swept before this one, its done flag not raised yet
+	while (c != SPH_KEY_NONE) {
+		const uint32_t cNext = cell_of_ticket(__shfl_sync(0xffffffffu, ticketAfter, 0)); // the load is consumed after this cell
+		ticketAfter = draw_ticket();
 		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
 		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
 		uint32_t lo[3], cnt[3];
@@ -841,8 +880,13 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		b.ownLo = cellStart[c];
 		b.m = cellStart[c + 1] - b.ownLo;
 		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		// The previous cell's done flag goes up only now: its write-back has had the time of the lookups above to
+		// reach L2, so the release seldom waits.  One lane releases for the warp (the __syncwarp that ended the
+		// write-back orders every lane's stores before it).
+		if (published != SPH_KEY_NONE && lane == 0) st_release_gpu(flow + 1 + published, 1u);
 		// wait for the occupied lower-colour cells of the 5x5 neighbourhood: lane l looks after cell (l%5-2, l/5-2)
 		{
+			const int color = (int)(((uint32_t)(yl + g.rowLo) % 3u) * 3u + (uint32_t)cx % 3u);
 			const uint32_t *flag = nullptr;
 			if (lane < 25u && lane != 12u) {
 				const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
@@ -866,12 +910,11 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
 			atomicOr(&ctr->overflow, 4u);
 		}
-		// publish: every lane fences its own stores, the warp joins, then one lane raises the flag
-		asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		__syncwarp();
-		if (lane == 0) st_release_gpu(flow + 1 + c, 1u);
-		ticket = __shfl_sync(0xffffffffu, nextTicket, 0);
+		published = c;
+		c = cNext;
 	}
+	if (published != SPH_KEY_NONE && lane == 0) st_release_gpu(flow + 1 + published, 1u);
 }
 
 // ---- the same sweep with a whole thread block per cell --------------------------------------------

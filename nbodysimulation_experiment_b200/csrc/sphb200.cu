@@ -567,7 +567,7 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	CU(s, cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
 	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 1 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
 	CU(s, cudaMalloc(&s->rowColor, (size_t)(g.rowHi - g.rowLo) * 3 * sizeof(uint32_t)));
 	return SPH_OK;
 }
