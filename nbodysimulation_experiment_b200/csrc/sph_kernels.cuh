@@ -356,21 +356,33 @@ __global__ void __launch_bounds__(SPH_THREADS) scan_add_kernel(uint32_t *__restr
 // order), and the same warps write the cells behind their offset.  Deterministic as a side effect.
 #define SPH_ROWLIST_WARPS 6 // two rows (x three column classes) per block
 
-__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ rowColor) {
+// Also resets the done flags of the one-launch sweep for this grid: 0 = occupied, not swept in any pass yet;
+// SPH_FLOW_EMPTY = nothing to wait for, ever.  (flow[0..1] are the ticket counters, the flags start at flow + 2.)
+#define SPH_FLOW_EMPTY 0xFFFFFFFFu
+#define SPH_FLOW_FLAGS 2u
+__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ rowColor,
+                                                                                uint32_t *__restrict__ flow) {
 	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
 	if (wid >= nRows * 3u) return;
 	const uint32_t row = wid / 3u, a = wid - row * 3u;
 	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
+	uint32_t *flags = flow + SPH_FLOW_FLAGS + (size_t)row * (uint32_t)g.gx;
 	uint32_t n = 0;
-	for (uint32_t cx = a + 3u * lane; cx < (uint32_t)g.gx; cx += 96u) n += cc[cx] ? 1u : 0u;
+	for (uint32_t cx = a + 3u * lane; cx < (uint32_t)g.gx; cx += 96u) {
+		const bool occ = cc[cx] != 0u;
+		flags[cx] = occ ? 0u : SPH_FLOW_EMPTY;
+		n += occ ? 1u : 0u;
+	}
 	n = warp_sum(n);
 	if (lane == 0) rowColor[wid] = n;
 }
 
 // nine warps, one per colour k = (row mod 3)*3 + a: exclusive scan of rowColor over that colour's rows, in place
-__global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount) {
+__global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount,
+                                                                 uint32_t *__restrict__ flow) {
 	const uint32_t k = threadIdx.x >> 5, lane = lane_id();
+	if (threadIdx.x < 2) flow[threadIdx.x] = 0u; // ticket counters of the next two passes over this grid
 	const uint32_t b = k / 3u, a = k - b * 3u;
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
 	const uint32_t r0 = (b + 3u - (uint32_t)g.rowLo % 3u) % 3u; // first local row whose global row is b mod 3
@@ -607,9 +619,13 @@ struct SweepBlock {
 
 // COHERENT: the staging loads bypass L1 (ld.global.cg) because another SM may have rewritten the
 // block earlier in the SAME launch (color_sweep_flow_kernel); the per-colour kernels read through L1.
-template <class M, int PASS, bool STAGED, bool COHERENT = false>
+// beforeWriteBack() runs once, after the last particle of the cell and before the block is written back.
+struct SweepNoHook {
+	__device__ __forceinline__ void operator()() const {}
+};
+template <class M, int PASS, bool STAGED, bool COHERENT = false, class Hook = SweepNoHook>
 __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock &b, float2 *pos, float2 *vel, const float2 *__restrict__ press,
-                                           float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask) {
+                                           float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask, Hook beforeWriteBack = Hook()) {
 	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
 	const uint32_t Tpad = (b.T + 31u) & ~31u;
 	if (STAGED) {
@@ -730,6 +746,7 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 			__syncwarp();
 		}
 	}
+	beforeWriteBack();
 	if (STAGED) {
 		for (uint32_t t = lane; t < b.T; t += 32) state[b.gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
 		__syncwarp();
@@ -798,8 +815,8 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 // reads exactly the state it reads in the nine-launch version and the results are bit-identical.
 // Deadlock-free: tickets are handed out in queue order and a warp works its tickets in order, so the
 // unfinished cell with the lowest ticket only waits for finished ones and its warp is running it.
-// `flow[0]` is the ticket counter and `flow[1 + cell]` the done flag; the host zeroes both before
-// the launch.  Loads of particle state bypass L1 (another SM may have just rewritten it).
+// `flow[0..1]` are ticket counters and `flow[2 + cell]` the done flags, (re)initialised with every grid build
+// (color_rows_count_kernel).  Loads of particle state bypass L1 (another SM may have just rewritten it).
 #define SPH_FLOW_WARPS 4
 #define SPH_FLOW_MIN_BLOCKS 10 // 48 registers: at 40 (12 blocks) ptxas rematerialises addresses inside the pair loops, +26 % instructions (ncu, r1b)
 
@@ -814,7 +831,7 @@ template <class M, int PASS>
 __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
     color_sweep_flow_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ colorList, uint32_t listStride,
                             const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
-                            Counters *__restrict__ ctr, uint32_t *flow) {
+                            Counters *__restrict__ ctr, uint32_t *flow, uint32_t epoch) {
 	extern __shared__ __align__(16) unsigned char sweepSmem[];
 	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
 	unsigned char *mine = sweepSmem + (size_t)w * sweep_bytes_per_warp(cap, PASS);
@@ -824,20 +841,29 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
 	const int nRows = g.rowHi - g.rowLo;
-	// Tickets are drawn two cells ahead and the cell behind the next ticket is looked up one cell ahead, so that
-	// neither the atomic's round trip nor the list lookup sits on a cell's critical path.  Lane 1 increments a per-warp decoy
-	// word alongside on purpose: on an address it can prove uniform, ptxas warp-aggregates the atomic (atom.inc and
-	// run-time increments too) and broadcasts, i.e. waits for, its result on the spot.
 	__shared__ uint32_t counts[9]; // cells per colour: shared memory, nine registers per thread would cost occupancy
 	if (threadIdx.x < 9) counts[threadIdx.x] = colorCount[threadIdx.x];
-	const uint32_t decoy = 1u + g.nCells + (blockIdx.x * SPH_FLOW_WARPS + w); // one word per warp behind the flags
 	__syncthreads();
+	// `epoch` counts the sweeps over this grid (1 = the displacement pass right after the grid build, 2 = the next
+	// step's viscosity pass, more only through sph_run_pass): a cell is done once its flag >= epoch, so the flags
+	// need no reset between passes; passes alternate between two ticket counters and zero the other one.
+	uint32_t *tickets = flow + (epoch & 1u);
+	if (blockIdx.x == 0 && threadIdx.x == 0) flow[(epoch + 1u) & 1u] = 0u;
+	uint32_t *flags = flow + SPH_FLOW_FLAGS;
+	// The next ticket is drawn when a cell's arithmetic is over, just before its write-back, and read after the
+	// done flag is up: the atomic's round trip overlaps the stores'.  Drawing it any earlier would hide it as well
+	// but park cells: every ticket a warp holds without working on it widens the window of cells in flight, and
+	// once that window exceeds a colour's list, cells start before the lower-colour neighbours they wait for
+	// (measured: two tickets ahead = 8 % of the cells wait, profiles/).  Lane 1 increments a per-warp decoy word
+	// alongside on purpose: on an address it can prove uniform, ptxas warp-aggregates the atomic (atom.inc and
+	// run-time increments too) and broadcasts, i.e. waits for, its result on the spot.
+	const uint32_t decoy = SPH_FLOW_FLAGS + g.nCells + (blockIdx.x * SPH_FLOW_WARPS + w); // one word per warp behind the flags
 	auto draw_ticket = [&]() -> uint32_t {
 		uint32_t t = 0;
-		if (lane < 2u) asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(flow + (lane == 0u ? 0u : decoy)) : "memory");
+		if (lane < 2u) asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(tickets + (lane == 0u ? 0u : decoy)) : "memory");
 		return t; // valid in lane 0
 	};
-	// queue position -> cell (SPH_KEY_NONE past the end); the colour is recomputed from the cell where needed
+	// queue position -> cell (SPH_KEY_NONE past the end)
 	auto cell_of_ticket = [&](uint32_t t) -> uint32_t {
 		uint32_t seen = 0, at = 0xffffffffu, base = 0;
 #pragma unroll
@@ -851,11 +877,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		return at == 0xffffffffu ? SPH_KEY_NONE : __ldg(&colorList[(size_t)base + at]);
 	};
 	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0));
-	uint32_t ticketAfter = draw_ticket(); // lane 0; consumed one iteration later
-	uint32_t published = SPH_KEY_NONE;    // the cell swept before this one, its done flag not raised yet
 	while (c != SPH_KEY_NONE) {
-		const uint32_t cNext = cell_of_ticket(__shfl_sync(0xffffffffu, ticketAfter, 0)); // the load is consumed after this cell
-		ticketAfter = draw_ticket();
 		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
 		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
 		uint32_t lo[3], cnt[3];
@@ -870,6 +892,19 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
 			}
 		}
+		const uint32_t ownLo = cellStart[c], ownHi = cellStart[c + 1];
+		// The lower-colour cells of the 5x5 neighbourhood must be done (empty ones always are): lane l looks after cell
+		// (l%5-2, l/5-2).  The flag is fetched together with the loads above: one round trip to L2 for all of them.
+		const uint32_t *flag = nullptr;
+		{
+			const int color = (int)(((uint32_t)(yl + g.rowLo) % 3u) * 3u + (uint32_t)cx % 3u);
+			const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
+			if (lane < 25u && lane != 12u && nx >= 0 && nx < g.gx && ny >= 0 && ny < nRows) {
+				const int ncolor = (int)(((uint32_t)(ny + g.rowLo) % 3u) * 3u + (uint32_t)nx % 3u);
+				const uint32_t *f = flags + ((uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx);
+				if (ncolor < color && ld_acquire_gpu(f) < epoch) flag = f;
+			}
+		}
 		SweepBlock b;
 		b.lo0 = lo[0];
 		b.lo1 = lo[1];
@@ -877,44 +912,29 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		b.off1 = cnt[0];
 		b.off2 = cnt[0] + cnt[1];
 		b.T = b.off2 + cnt[2];
-		b.ownLo = cellStart[c];
-		b.m = cellStart[c + 1] - b.ownLo;
+		b.ownLo = ownLo;
+		b.m = ownHi - ownLo;
 		b.ownOff = b.off1 + (b.ownLo - lo[1]);
-		// The previous cell's done flag goes up only now: its write-back has had the time of the lookups above to
-		// reach L2, so the release seldom waits.  One lane releases for the warp (the __syncwarp that ended the
-		// write-back orders every lane's stores before it).
-		if (published != SPH_KEY_NONE && lane == 0) st_release_gpu(flow + 1 + published, 1u);
-		// wait for the occupied lower-colour cells of the 5x5 neighbourhood: lane l looks after cell (l%5-2, l/5-2)
-		{
-			const int color = (int)(((uint32_t)(yl + g.rowLo) % 3u) * 3u + (uint32_t)cx % 3u);
-			const uint32_t *flag = nullptr;
-			if (lane < 25u && lane != 12u) {
-				const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
-				if (nx >= 0 && nx < g.gx && ny >= 0 && ny < nRows) {
-					const int ncolor = (int)(((uint32_t)(ny + g.rowLo) % 3u) * 3u + (uint32_t)nx % 3u);
-					const uint32_t nc = (uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx;
-					if (ncolor < color && cellStart[nc + 1u] > cellStart[nc]) flag = flow + 1 + nc;
-				}
-			}
-			for (;;) {
-				if (flag && ld_acquire_gpu(flag) != 0u) flag = nullptr;
-				if (__all_sync(0xffffffffu, flag == nullptr)) break;
-				__nanosleep(200);
-			}
-			__syncwarp();
-		}
-		if (((b.T + 31u) & ~31u) <= cap) {
-			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask);
-		} else if (b.T <= wideCap) {
-			sweep_cell<M, PASS, false, true>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask);
-		} else if (lane == 0) { // denser than anything the queue can hold: report, leave the cell alone
-			atomicOr(&ctr->overflow, 4u);
+		while (!__all_sync(0xffffffffu, flag == nullptr)) {
+			__nanosleep(100);
+			if (flag && ld_acquire_gpu(flag) >= epoch) flag = nullptr;
 		}
 		__syncwarp();
-		published = c;
-		c = cNext;
+		uint32_t nextTicket = 0;
+		auto draw_next = [&]() { nextTicket = draw_ticket(); };
+		if (((b.T + 31u) & ~31u) <= cap) {
+			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask, draw_next);
+		} else if (b.T <= wideCap) {
+			sweep_cell<M, PASS, false, true>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask, draw_next);
+		} else { // denser than anything the queue can hold: report, leave the cell alone
+			if (lane == 0) atomicOr(&ctr->overflow, 4u);
+			draw_next();
+		}
+		// done: one lane releases for the warp (the __syncwarp orders every lane's write-back before it)
+		__syncwarp();
+		if (lane == 0) st_release_gpu(flags + c, epoch);
+		c = cell_of_ticket(__shfl_sync(0xffffffffu, nextTicket, 0));
 	}
-	if (published != SPH_KEY_NONE && lane == 0) st_release_gpu(flow + 1 + published, 1u);
 }
 
 // ---- the same sweep with a whole thread block per cell --------------------------------------------

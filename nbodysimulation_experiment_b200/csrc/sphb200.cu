@@ -93,13 +93,13 @@ enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DEN
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
 struct StepGraphKey {
-	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, parts;
+	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, parts, flowEpoch;
 	float2 force;
 	PairParams k;
 };
 struct StepGraph {
 	StepGraphKey key;
-	uint32_t parityAfter = 0;
+	uint32_t parityAfter = 0, flowEpochAfter = 0;
 	cudaGraphExec_t exec = nullptr;
 };
 
@@ -128,7 +128,8 @@ struct SphSim {
 	// occupied cells per colour for the coloured Gauss-Seidel sweeps
 	uint32_t *colorCount = nullptr, *colorList = nullptr;
 	uint32_t *rowColor = nullptr;  // occupied cells per (local row, cx mod 3), then their offsets in the colour lists
-	uint32_t *sweepFlow = nullptr; // [0] ticket counter, [1 + cell] done flag of the one-launch sweep (color_sweep_flow_kernel)
+	uint32_t *sweepFlow = nullptr; // [0..1] ticket counters, [2 + cell] done flags of the one-launch sweep (color_sweep_flow_kernel), then decoy words
+	uint32_t flowEpoch = 0;        // sweeps launched over the current grid (the flags count passes, see color_sweep_flow_kernel)
 	uint32_t listStride = 0, sweepCap = 512;
 	bool sweepAdaptive = true;       // pick the staging capacity from the candidate-list maximum of recent steps
 	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
@@ -426,8 +427,9 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
 	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) { // occupied cells per colour, each list in row-major order
 		const unsigned rowWarps = (unsigned)(g.rowHi - g.rowLo) * 3u, rowBlocks = (rowWarps + SPH_ROWLIST_WARPS - 1) / SPH_ROWLIST_WARPS;
-		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor);
-		color_rows_scan_kernel<<<1, 9 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount);
+		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->sweepFlow);
+		color_rows_scan_kernel<<<1, 9 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount, s->sweepFlow);
+		s->flowEpoch = 0; // the done flags are fresh: the next sweep over this grid is its first
 		color_rows_fill_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->colorList, s->listStride);
 	}
 	if (timed) record_phase(s, PH_SCAN + 1);
@@ -499,9 +501,8 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 		const int occBlocks = std::max(1, flowBlocksPerSM[std::min(96u, (s->sweepCap + 31u) / 32u)]);
 		const uint64_t want = (9 * cells + SPH_FLOW_WARPS - 1) / SPH_FLOW_WARPS;
 		const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
-		cudaMemsetAsync(s->sweepFlow, 0, ((size_t)s->grid.nCells + 1) * sizeof(uint32_t), s->stream);
 		color_sweep_flow_kernel<M, PASS><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
-		                                                                                 s->vel.in(), s->press.in(), s->sweepCap, s->dCtr, s->sweepFlow);
+		                                                                                 s->vel.in(), s->press.in(), s->sweepCap, s->dCtr, s->sweepFlow, ++s->flowEpoch);
 		return;
 	}
 	for (int color = 0; color < 9; ++color) {
@@ -567,7 +568,11 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	CU(s, cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
 	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 1 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
+	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 2 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
+	CU(s, cudaMemset(s->sweepFlow, 0xFF, ((size_t)g.nCells + 2 + 65536) * sizeof(uint32_t))); // no grid yet: every cell empty
+	CU(s, cudaMemset(s->sweepFlow, 0, 2 * sizeof(uint32_t)));
+	if (s->colorCount) CU(s, cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
+	s->flowEpoch = 0;
 	CU(s, cudaMalloc(&s->rowColor, (size_t)(g.rowHi - g.rowLo) * 3 * sizeof(uint32_t)));
 	return SPH_OK;
 }
@@ -912,6 +917,7 @@ int sph_clear_particles(SphHandle s) {
 	s->steppedOnce = false;
 	set_counts_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, 0, 0);
 	CU(s, cudaMemsetAsync(s->cellStart, 0, ((size_t)s->grid.nCells + 1) * sizeof(uint32_t), s->stream));
+	CU(s, cudaMemsetAsync(s->colorCount, 0, 9 * sizeof(uint32_t), s->stream)); // no occupied cells: the sweeps have nothing to visit
 	CU(s, cudaGetLastError());
 	return SPH_OK;
 }
@@ -1252,6 +1258,7 @@ int sph_step(SphHandle s, float dt) {
 		key.nbodies = (uint32_t)s->bodies.size();
 		key.haloMsgRecords = s->haloMsgRecords;
 		key.parts = (uint32_t)parts;
+		key.flowEpoch = s->flowEpoch; // the sweep launches carry the pass number over the current grid as an argument
 		key.force = force;
 		key.k = k;
 		StepGraph *g = nullptr;
@@ -1271,6 +1278,7 @@ int sph_step(SphHandle s, float dt) {
 			StepGraph made;
 			made.key = key;
 			made.parityAfter = buffer_parity(s);
+			made.flowEpochAfter = s->flowEpoch;
 			CU(s, cudaGraphInstantiate(&made.exec, graph, 0));
 			cudaGraphDestroy(graph);
 			set_buffer_parity(s, key.parity); // capture only recorded the launches: the state is still "before"
@@ -1279,6 +1287,7 @@ int sph_step(SphHandle s, float dt) {
 		}
 		CU(s, cudaGraphLaunch(g->exec, s->stream));
 		set_buffer_parity(s, g->parityAfter);
+		s->flowEpoch = g->flowEpochAfter;
 		return SPH_OK;
 	};
 	if (s->cfg.world_size == 1) {

@@ -207,19 +207,23 @@ def test_collision_pass_bitwise(pkg):
     gpu.close()
 
 
-@pytest.mark.parametrize("solver", ["gs", "gather"])
+@pytest.mark.parametrize("solver", ["gs", "gs-flow", "gs-warp", "gather"])
 def test_viscosity_and_delta_passes_bitwise(pkg, solver):
-    """Per-pass parity from an injected state (a reference dump, mid-splash)."""
+    """Per-pass parity from an injected state (a reference dump, mid-splash).  The passes run twice over the same
+    grid: the one-launch sweep numbers its passes over a grid (done flags count them), so a third and fourth pass
+    must still wait for their neighbours."""
     g = np.load(os.path.join(GOLDEN_DIR, "scene1.npz"))
     state = g["state32"]
-    gpu = pkg.ParticleSimulation(solver=pkg.SPH_SOLVER_COLORED_GS if solver == "gs" else pkg.SPH_SOLVER_GATHER)
-    cpu = CpuSim("oracle", mode=MODE_COLORED if solver == "gs" else MODE_JACOBI)
+    flags = {"gs-flow": pkg._lib.SPH_FLAG_SWEEP_FLOW, "gs-warp": pkg._lib.SPH_FLAG_SWEEP_WARP}.get(solver, 0)
+    gpu = pkg.ParticleSimulation(solver=pkg.SPH_SOLVER_GATHER if solver == "gather" else pkg.SPH_SOLVER_COLORED_GS, flags=flags)
+    cpu = CpuSim("oracle", mode=MODE_JACOBI if solver == "gather" else MODE_COLORED)
     gpu.LoadScenario(1, seed=1)
     cpu.load_scenario(1, 1)
     gpu.put_particles(state)
     cpu.put_particles(state)
     cpu.pass_neighbor_search()
     for which, run in ((pkg._lib.PASS_VISCOSITY, lambda: cpu.pass_viscosity(DT)), (pkg._lib.PASS_DENSITY, cpu.pass_density),
+                       (pkg._lib.PASS_DELTA, lambda: cpu.pass_delta(DT)), (pkg._lib.PASS_VISCOSITY, lambda: cpu.pass_viscosity(DT)),
                        (pkg._lib.PASS_DELTA, lambda: cpu.pass_delta(DT))):
         gpu.RunPass(which, DT)
         run()
