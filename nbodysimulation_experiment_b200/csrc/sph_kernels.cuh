@@ -369,10 +369,18 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kerne
 	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
 	uint32_t *flags = flow + SPH_FLOW_FLAGS + (size_t)row * (uint32_t)g.gx;
 	uint32_t n = 0;
-	for (uint32_t cx = a + 3u * lane; cx < (uint32_t)g.gx; cx += 96u) {
-		const bool occ = cc[cx] != 0u;
-		flags[cx] = occ ? 0u : SPH_FLOW_EMPTY;
-		n += occ ? 1u : 0u;
+	for (uint32_t c0 = a + 3u * lane; c0 < (uint32_t)g.gx; c0 += 4u * 96u) { // four loads in flight per round trip
+		uint32_t v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) v[u] = (c0 + 96u * (uint32_t)u < (uint32_t)g.gx) ? cc[c0 + 96u * (uint32_t)u] : 0u;
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t cx = c0 + 96u * (uint32_t)u;
+			if (cx < (uint32_t)g.gx) {
+				flags[cx] = v[u] ? 0u : SPH_FLOW_EMPTY;
+				n += v[u] ? 1u : 0u;
+			}
+		}
 	}
 	n = warp_sum(n);
 	if (lane == 0) rowColor[wid] = n;
@@ -387,17 +395,25 @@ __global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uin
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
 	const uint32_t r0 = (b + 3u - (uint32_t)g.rowLo % 3u) % 3u; // first local row whose global row is b mod 3
 	uint32_t running = 0;
-	for (uint32_t base = r0; base < nRows; base += 96u) {
-		const uint32_t row = base + 3u * lane;
-		const uint32_t v = row < nRows ? rowColor[row * 3u + a] : 0u;
-		uint32_t inc = v;
+	for (uint32_t base = r0; base < nRows; base += 4u * 96u) { // four loads in flight per round trip
+		uint32_t v[4];
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-			if ((int)lane >= o) inc += up;
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t row = base + 96u * (uint32_t)u + 3u * lane;
+			v[u] = row < nRows ? rowColor[row * 3u + a] : 0u;
 		}
-		if (row < nRows) rowColor[row * 3u + a] = running + inc - v;
-		running += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t row = base + 96u * (uint32_t)u + 3u * lane;
+			uint32_t inc = v[u];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+				if ((int)lane >= o) inc += up;
+			}
+			if (row < nRows) rowColor[row * 3u + a] = running + inc - v[u];
+			running += __shfl_sync(0xffffffffu, inc, 31);
+		}
 	}
 	if (lane == 0) colorCount[k] = running;
 }
@@ -412,12 +428,21 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel
 	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
 	uint32_t *list = colorList + (size_t)k * listStride;
 	uint32_t at = rowColor[wid];
-	for (uint32_t c0 = a; c0 < (uint32_t)g.gx; c0 += 96u) { // warp-uniform trip count
-		const uint32_t cx = c0 + 3u * lane;
-		const bool occ = cx < (uint32_t)g.gx && cc[cx] != 0u;
-		const uint32_t mask = __ballot_sync(0xffffffffu, occ);
-		if (occ) list[at + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = row * (uint32_t)g.gx + cx;
-		at += (uint32_t)__popc(mask);
+	for (uint32_t c0 = a; c0 < (uint32_t)g.gx; c0 += 4u * 96u) { // warp-uniform trip count, four loads in flight per round trip
+		uint32_t v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t cx = c0 + 96u * (uint32_t)u + 3u * lane;
+			v[u] = cx < (uint32_t)g.gx ? cc[cx] : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint32_t cx = c0 + 96u * (uint32_t)u + 3u * lane;
+			const bool occ = v[u] != 0u;
+			const uint32_t mask = __ballot_sync(0xffffffffu, occ);
+			if (occ) list[at + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = row * (uint32_t)g.gx + cx;
+			at += (uint32_t)__popc(mask);
+		}
 	}
 }
 
@@ -469,11 +494,14 @@ __global__ void __launch_bounds__(SPH_THREADS) reorder_kernel(GridDesc g, Counte
 		occMin = min(occMin, hi - lo);
 		occMax = max(occMax, hi - lo);
 	}
+	// Running min/max of the cell occupancy (demo4.cpp:64-67).  One atomic per warp on the same two words is
+	// 65 000 serialised L2 atomics per step at 1M particles - they alone took 50 of this kernel's 59 us (ncu, r1e).
+	// Both values converge after a few warps, so look first (a stale value only costs a redundant atomic).
 	occMin = warp_min(occMin);
 	occMax = warp_max(occMax);
 	if (lane_id() == 0 && occMax) {
-		atomicMin(&ctr->minCell, occMin);
-		atomicMax(&ctr->maxCell, occMax);
+		if (occMin < __ldcg(&ctr->minCell)) atomicMin(&ctr->minCell, occMin);
+		if (occMax > __ldcg(&ctr->maxCell)) atomicMax(&ctr->maxCell, occMax);
 	}
 }
 
@@ -499,14 +527,20 @@ __global__ void __launch_bounds__(SPH_THREADS) density_kernel(GridDesc g, PairPa
 		cSum += cand;
 	}
 	// neighbour statistics of demo4.cpp:369-376
+	// (looked at before the atomic for the same reason as in reorder_kernel; the sum goes through one word per block)
+	__shared__ unsigned long long blockSum;
+	if (threadIdx.x == 0) blockSum = 0ull;
+	__syncthreads();
 	cMin = warp_min(cMin);
 	cMax = warp_max(cMax);
 	cSum = warp_sum(cSum);
 	if (lane_id() == 0 && cMax) {
-		atomicMin(&ctr->minNbr, cMin);
-		atomicMax(&ctr->maxNbr, cMax);
-		atomicAdd(&ctr->pairCandidates, (unsigned long long)cSum);
+		if (cMin < __ldcg(&ctr->minNbr)) atomicMin(&ctr->minNbr, cMin);
+		if (cMax > __ldcg(&ctr->maxNbr)) atomicMax(&ctr->maxNbr, cMax);
+		atomicAdd(&blockSum, (unsigned long long)cSum);
 	}
+	__syncthreads();
+	if (threadIdx.x == 0 && blockSum) atomicAdd(&ctr->pairCandidates, blockSum);
 }
 
 // ---- phase 7: pressure displacement, gather form of demo4.cpp:239-255 ---------------------------
