@@ -3,7 +3,8 @@
     python tools/summarize_ncu.py launches gpurun_out/launches.csv  profiles/rN_launches_<what>.txt  "<command that was profiled>"
     python tools/summarize_ncu.py kernels  gpurun_out/prof.ncu-rep   profiles/rN_kernels_<what>.txt   "<command that was profiled>"
 
-`launches`: the CSV log of `ncu --metrics gpu__time_duration.sum --clock-control none --csv`; prints the
+`traffic`: per-kernel DRAM bytes and duration per launch of a `--set full` report as JSON (profiles/rN_traffic*.json, read by
+bench.py for roofline.traffic).  `launches`: the CSV log of `ncu --metrics gpu__time_duration.sum --clock-control none --csv`; prints the
 share of the step every kernel takes.  `kernels`: a `--set full` report; prints, per captured launch,
 duration, DRAM bytes, issue-slot utilisation, pipe utilisation, lane efficiency, occupancy limits and the
 top warp-stall reasons.
@@ -89,8 +90,35 @@ def kernels(src, dst, what):
             f.write(f"   {'warp stall samples (top)':42s} {top}\n")
 
 
+def traffic(src, dst, what):
+    """dram__bytes_read.sum + dram__bytes_write.sum and duration per launch of every captured kernel -> JSON (bench.py's roofline.traffic)"""
+    import json
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("sphb200::", "").replace("(int)", "")
+        b = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            b += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        i = hdr.index("gpu__time_duration.sum")
+        t = float(r[i].replace(",", "")) * tscale.get(units[i], 1.0)
+        a = agg.setdefault(name, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += b
+        a[2] += t
+    out = {k: {"launches_captured": c, "dram_bytes_per_launch": b / c, "duration_us_per_launch": t / c} for k, (c, b, t) in agg.items()}
+    out["_source"] = what
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     what = sys.argv[4] if len(sys.argv) > 4 else ""
-    (launches if mode == "launches" else kernels)(src, dst, what)
+    {"launches": launches, "kernels": kernels, "traffic": traffic}[mode](src, dst, what)
     print(open(dst).read())
