@@ -218,12 +218,13 @@ def run_ours(args):
     if world == 1:
         frames = [(pinned_empty((n_total, 2), np.float32), pinned_empty((n_total, 4), np.float32)) for _ in range(2)]
     else:
-        owned_bufs = sim.owned_buffers(records=False, render=True, pinned=True)
+        owned_bufs = [sim.owned_buffers(records=False, render=True, pinned=True) for _ in range(2)]
     if world == 1:  # untimed warm-up frame: the first Render allocates the device-side snapshot
         sim.Render(frames[1][0][0], frames[1][1][0], wait=False)
         sim.WaitRender()
-    else:
-        sim.read_owned(records=False, render=True, buffers=owned_bufs)
+    else:  # (and on strips it learns how many particles a frame ships)
+        sim.render_owned(owned_bufs[1])
+        sim.wait_render_owned()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -235,10 +236,16 @@ def run_ours(args):
             sim.Render(pos_host, col_host, wait=False)  # snapshot + D2H on the copy stream
             d2h = n_total * 24
         else:
-            got = sim.read_owned(records=False, render=True, buffers=owned_bufs)
-            d2h = len(got["ids"]) * 28
+            got = sim.wait_render_owned()  # frame k-1 (None before the first one)
+            sim.render_owned(owned_bufs[k % 2])  # snapshot + D2H on the copy stream, overlapped with Update k+1
+            if got is not None:
+                d2h = len(got["ids"]) * 28
     if world == 1:
         sim.WaitRender()
+    else:
+        got = sim.wait_render_owned()
+        d2h = len(got["ids"]) * 28
+        assert np.isfinite(got["positions"]).all() and (got["colors"][:, 3] == 1.0).all()
     barrier()
     e2e_s = all_max(time.perf_counter() - t0)
     e2e_value = n_total * e2e_steps / e2e_s
@@ -307,7 +314,7 @@ def run_ours(args):
                        "parallelism": f"ystrip{world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4" + (" + id" if world > 1 else "") + ") to host memory every step"
-                            + ("; double-buffered pinned frames, the copy of frame k overlaps Update k+1" if world == 1 else "")},
+                            + "; double-buffered pinned frames, the copy of frame k overlaps Update k+1"},
             "gpu_launches": KERNELS_PER_STEP["gather" if args.solver == "gather" else ("gs" if (args.sweep == "flow" or (args.sweep == "auto" and (world > 1 or n_local >= 131072))) else "gs9")] * args.steps,
             "clocks": clocks,
             "roofline": roofline,

@@ -219,6 +219,12 @@ int sph_get_strip(SphHandle h, int32_t *row_begin, int32_t *row_end);
  * *count receives the number of owned particles.  Works for world_size = 1 too. */
 int sph_read_owned(SphHandle h, uint32_t *ids, void *records, size_t record_stride, void *positions, size_t pos_stride,
                    void *colors, size_t color_stride, uint64_t *count);
+/* The same readback for the renderer, overlapped like sph_render_particles (demo4.cpp:520-531 on a strip): the
+ * snapshot is taken on the simulation's stream, the copies run on a second stream while the next sph_step
+ * executes, and the host arrays are complete after sph_wait_render_owned, which also returns the count.  One frame
+ * in flight; alternate two sets of (pinned) host arrays to overlap a frame's copy with the next step. */
+int sph_render_owned(SphHandle h, uint32_t *ids, void *positions, size_t pos_stride, void *colors, size_t color_stride);
+int sph_wait_render_owned(SphHandle h, uint64_t *count);
 
 #ifdef __cplusplus
 }

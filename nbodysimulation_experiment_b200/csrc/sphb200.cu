@@ -156,6 +156,13 @@ struct SphSim {
 	uint64_t exchanges = 0;
 	NcclComm comm = nullptr;
 	uint32_t *dOwnedCount = nullptr, *dOwnedIds = nullptr;
+	// overlapped strip readback (sph_render_owned / sph_wait_render_owned)
+	uint32_t *hOwnedCount = nullptr; // pinned
+	uint64_t ownedShipped = 0, ownedLast = 0;
+	uint32_t *ownedIdsDst = nullptr;
+	void *ownedPosDst = nullptr, *ownedColDst = nullptr;
+	size_t ownedPosStride = 0, ownedColStride = 0;
+	bool ownedPending = false;
 
 	uint64_t hostN = 0;        // particles this rank holds (exact on one GPU; an upper bound on strips)
 	uint64_t nextId = 0;       // creation counter
@@ -812,6 +819,7 @@ int sph_destroy(SphHandle s) {
 	for (StepGraph &g : s->graphs)
 		if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (s->hCtrLag) cudaFreeHost(s->hCtrLag);
+	if (s->hOwnedCount) cudaFreeHost(s->hOwnedCount);
 	if (s->lagEvent) cudaEventDestroy(s->lagEvent);
 	for (auto &e : s->phaseEv)
 		if (e) cudaEventDestroy(e);
@@ -1629,6 +1637,78 @@ int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, 
 	CU(s, cudaStreamSynchronize(s->stream));
 	return SPH_OK;
 }
+// The strip counterpart of sph_render_particles: snapshot of the owned particles (ids, positions, colours) on the
+// simulation's stream, device-to-host copies on the copy stream, so the next sph_step overlaps them.  The number of
+// owned particles only exists on the device; the copies ship 1.1 x the previous frame's count (+4096) and
+// sph_wait_render_owned fetches the rest in the rare frame that outgrew it.  The first frame is read synchronously.
+int sph_render_owned(SphHandle s, uint32_t *ids, void *positions, size_t posStride, void *colors, size_t colStride) {
+	CHECK_HANDLE(s);
+	if (!ids || !positions || !colors) return fail(s, SPH_ERR_INVALID, "sph_render_owned needs ids, positions and colours");
+	if (posStride < sizeof(float2) || colStride < sizeof(float4)) return fail(s, SPH_ERR_INVALID, "stride too small");
+	if (s->ownedPending) return fail(s, SPH_ERR_STATE, "sph_wait_render_owned was not called for the previous frame");
+	const size_t cap = s->capacity;
+	if (!s->hOwnedCount) CU(s, cudaMallocHost(&s->hOwnedCount, sizeof(uint32_t)));
+	s->ownedIdsDst = ids;
+	s->ownedPosDst = positions;
+	s->ownedColDst = colors;
+	s->ownedPosStride = posStride;
+	s->ownedColStride = colStride;
+	if (s->ownedLast == 0) { // no estimate yet: synchronous read
+		uint64_t n = 0;
+		int rc = sph_read_owned(s, ids, nullptr, 0, positions, posStride, colors, colStride, &n);
+		if (rc != SPH_OK) return rc;
+		*s->hOwnedCount = (uint32_t)n;
+		s->ownedShipped = n;
+		s->ownedLast = std::max<uint64_t>(n, 1);
+		s->ownedPending = true;
+		return SPH_OK;
+	}
+	if (!s->dOwnedIds) CU(s, cudaMalloc(&s->dOwnedIds, cap * sizeof(uint32_t)));
+	if (!s->dRenderPos) {
+		CU(s, cudaMalloc(&s->dRenderPos, cap * sizeof(float2)));
+		CU(s, cudaMalloc(&s->dRenderCol, cap * sizeof(float4)));
+	}
+	// the device-side snapshot may only be overwritten once the previous frame's copies have left it
+	if (s->copyPending) CU(s, cudaStreamWaitEvent(s->stream, s->copyDone, 0));
+	CU(s, cudaMemsetAsync(s->dOwnedCount, 0, sizeof(uint32_t), s->stream));
+	gather_owned_kernel<<<blocks_for(s->hostN), SPH_THREADS, 0, s->stream>>>(s->grid, s->dCtr, s->id.in(), s->cellOf.in(), s->pos.in(), s->prev.in(), s->vel.in(),
+	                                                                       s->acc.in(), s->dens.in(), s->press.in(), s->params.rest_density, s->dOwnedCount,
+	                                                                       s->dOwnedIds, nullptr, s->dRenderPos, s->dRenderCol);
+	CU(s, cudaGetLastError());
+	CU(s, cudaEventRecord(s->renderReady, s->stream));
+	CU(s, cudaStreamWaitEvent(s->copyStream, s->renderReady, 0));
+	const uint64_t ship = std::min<uint64_t>(cap, s->ownedLast + s->ownedLast / 10 + 4096);
+	CU(s, cudaMemcpyAsync(s->hOwnedCount, s->dOwnedCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
+	CU(s, cudaMemcpyAsync(ids, s->dOwnedIds, (size_t)ship * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
+	CU(s, copy_strided(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), (size_t)ship, cudaMemcpyDeviceToHost, s->copyStream));
+	CU(s, copy_strided(colors, colStride, s->dRenderCol, sizeof(float4), sizeof(float4), (size_t)ship, cudaMemcpyDeviceToHost, s->copyStream));
+	CU(s, cudaEventRecord(s->copyDone, s->copyStream));
+	s->ownedShipped = ship;
+	s->copyPending = true;
+	s->ownedPending = true;
+	return SPH_OK;
+}
+
+int sph_wait_render_owned(SphHandle s, uint64_t *count) {
+	CHECK_HANDLE(s);
+	if (!s->ownedPending) return fail(s, SPH_ERR_STATE, "no sph_render_owned frame in flight");
+	if (s->copyPending) CU(s, cudaEventSynchronize(s->copyDone));
+	const uint64_t n = std::min<uint64_t>(*s->hOwnedCount, s->capacity);
+	if (n > s->ownedShipped) { // the strip grew by more than 10 % in one frame: fetch the tail (the snapshot is still intact)
+		const size_t from = (size_t)s->ownedShipped, more = (size_t)(n - s->ownedShipped);
+		CU(s, cudaMemcpyAsync(s->ownedIdsDst + from, s->dOwnedIds + from, more * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
+		CU(s, copy_strided((char *)s->ownedPosDst + from * s->ownedPosStride, s->ownedPosStride, s->dRenderPos + from, sizeof(float2), sizeof(float2), more,
+		                   cudaMemcpyDeviceToHost, s->copyStream));
+		CU(s, copy_strided((char *)s->ownedColDst + from * s->ownedColStride, s->ownedColStride, s->dRenderCol + from, sizeof(float4), sizeof(float4), more,
+		                   cudaMemcpyDeviceToHost, s->copyStream));
+		CU(s, cudaStreamSynchronize(s->copyStream));
+	}
+	s->ownedLast = std::max<uint64_t>(n, 1);
+	s->ownedPending = false;
+	if (count) *count = n;
+	return SPH_OK;
+}
+
 int sph_get_strip(SphHandle s, int32_t *rowBegin, int32_t *rowEnd) {
 	CHECK_HANDLE(s);
 	if (rowBegin) *rowBegin = s->grid.ownLo;

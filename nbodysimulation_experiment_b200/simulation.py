@@ -248,6 +248,24 @@ class ParticleSimulation:
             out["positions"], out["colors"] = pos[:k], col[:k]
         return out
 
+    def render_owned(self, buffers):
+        """Overlapped strip readback (sph_render_owned): enqueue the snapshot and its copies into `buffers`
+        (owned_buffers(render=True, pinned=True)); the arrays are complete after wait_render_owned()."""
+        ids, pos, col = buffers["ids"], buffers["positions"], buffers["colors"]
+        self._check(self._lib.sph_render_owned(self._h, ids.ctypes.data, pos.ctypes.data, pos.strides[0], col.ctypes.data, col.strides[0]))
+        self._owned_in_flight = buffers
+
+    def wait_render_owned(self):
+        """-> dict(ids, positions, colors) views of the frame enqueued by render_owned, or None if there is none."""
+        buffers = getattr(self, "_owned_in_flight", None)
+        if buffers is None:
+            return None
+        n = C.c_uint64()
+        self._check(self._lib.sph_wait_render_owned(self._h, C.byref(n)))
+        self._owned_in_flight = None
+        k = n.value
+        return {"ids": buffers["ids"][:k], "positions": buffers["positions"][:k], "colors": buffers["colors"][:k]}
+
     def owned_buffers(self, records=True, render=False, capacity=None, pinned=True):
         """Host arrays for read_owned (page-locked when pinned=True; keep the dict alive while in use)."""
         cap = int(capacity or self.config.max_particles)

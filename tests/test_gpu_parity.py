@@ -519,6 +519,31 @@ def test_graph_replay_is_bit_identical_to_plain_launches(pkg):
     assert_bits_equal(runs[0], runs[1], "graph vs plain")
 
 
+def test_overlapped_owned_readback_equals_the_synchronous_one(pkg):
+    """sph_render_owned / sph_wait_render_owned (the strip counterpart of Render, copies overlapped with the next
+    step) against sph_read_owned, on one GPU where a rank owns everything; emitters make the count grow between
+    frames, including by more than the 10 % head-room a frame ships (the tail fetch)."""
+    sim = pkg.ParticleSimulation()
+    sim.LoadScenario(5, seed=3)  # emitters + polygons
+    bufs = [sim.owned_buffers(records=False, render=True, pinned=True) for _ in range(2)]
+    sync = sim.owned_buffers(records=False, render=True, pinned=False)
+    for k in range(60):
+        sim.Update(DT)
+        if k == 30:  # a burst: +40 % particles in one frame
+            n = sim.GetParticleCount()
+            sim.AddParticles(np.random.default_rng(k).uniform(-1.0, 1.0, (max(n * 2 // 5, 50), 2)).astype(np.float32))
+        sim.render_owned(bufs[k % 2])
+        got = sim.wait_render_owned()
+        want = sim.read_owned(records=False, render=True, buffers=sync)  # same state: nothing stepped in between
+        assert len(got["ids"]) == len(want["ids"]) == sim.GetParticleCount()
+        a, b = np.argsort(got["ids"]), np.argsort(want["ids"])
+        assert np.array_equal(got["ids"][a], want["ids"][b])
+        assert_bits_equal(got["positions"][a], want["positions"][b], f"frame {k} positions")
+        assert_bits_equal(got["colors"][a], want["colors"][b], f"frame {k} colours")
+    assert sim.wait_render_owned() is None
+    sim.close()
+
+
 def test_two_gpu_strips_match_one_gpu_bitwise():
     """Runs tools/mgpu_check.py under torchrun when the box has two GPUs (the round-end box has one)."""
     import subprocess
