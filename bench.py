@@ -315,7 +315,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_blob.nbytes), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": "Update + Render readback (pos float2 + colour float4" + (" + id" if world > 1 else "") + ") to host memory every step"
                             + "; double-buffered pinned frames, the copy of frame k overlaps Update k+1"},
-            "gpu_launches": KERNELS_PER_STEP["gather" if args.solver == "gather" else ("gs" if (args.sweep == "flow" or (args.sweep == "auto" and (world > 1 or n_local >= 131072))) else "gs9")] * args.steps,
+            # strips add reset_halo, note_peak and one unpack per neighbour (rank 0 has one neighbour; NCCL's own kernels are not counted)
+            "gpu_launches": (KERNELS_PER_STEP["gather" if args.solver == "gather" else ("gs" if (args.sweep == "flow" or (args.sweep == "auto" and (world > 1 or n_local >= 131072))) else "gs9")]
+                             + (3 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
             "roofline": roofline,
             "phases_ms": phases,
