@@ -64,6 +64,38 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // acceleration (demo4.cpp:146), so `acc` is read from index accFrom on and zeroed.
 // Block 0 also opens the step: it resets the statistics that are per step in the reference
 // (demo4.cpp:369-370); nothing else in this kernel touches them.
+// The three streaming kernels (integrate, predict + key, collide + velocity) move 16-36 B per particle and do almost
+// no arithmetic: with one particle per thread there were ~2.4 MB of loads in flight per GPU where HBM needs ~6 MB
+// (6.4 TB/s x ~1 us), and they ran at 1.5-2 TB/s.  A thread now takes particle PAIRS (one 16-byte access per float2
+// array) and keeps two pairs in flight.
+struct Pair2 { // particles 2q and 2q+1 of a float2 array as one 16-byte access (the arrays are 256-byte aligned)
+	float2 a, b;
+};
+__device__ __forceinline__ Pair2 load_pair(const float2 *arr, uint32_t q, bool both) {
+	Pair2 r;
+	if (both) {
+		const float4 v = *reinterpret_cast<const float4 *>(arr + 2u * q);
+		r.a = make_float2(v.x, v.y);
+		r.b = make_float2(v.z, v.w);
+	} else {
+		r.a = arr[2u * q];
+		r.b = make_float2(0.0f, 0.0f);
+	}
+	return r;
+}
+__device__ __forceinline__ void store_pair(float2 *arr, uint32_t q, bool both, Pair2 v) {
+	if (both) *reinterpret_cast<float4 *>(arr + 2u * q) = make_float4(v.a.x, v.a.y, v.b.x, v.b.y);
+	else arr[2u * q] = v.a;
+}
+
+__device__ __forceinline__ float2 integrate_one(float2 v, float2 a, float2 force, float dt) {
+	a.x = __fadd_rn(force.x, a.x); // operator+= evaluates b + a (vecmath.h:249-252)
+	a.y = __fadd_rn(force.y, a.y);
+	v.x = __fadd_rn(__fmul_rn(a.x, dt), v.x);
+	v.y = __fadd_rn(__fmul_rn(a.y, dt), v.y);
+	return v;
+}
+
 __global__ void __launch_bounds__(SPH_THREADS) integrate_kernel(Counters *__restrict__ ctr, float2 *__restrict__ vel,
                                                                float2 *__restrict__ acc, uint32_t accFrom, float2 force, float dt) {
 	const uint32_t n = ctr->n;
@@ -72,19 +104,30 @@ __global__ void __launch_bounds__(SPH_THREADS) integrate_kernel(Counters *__rest
 		ctr->maxNbr = 0;
 		ctr->pairCandidates = 0ull;
 	}
-	SPH_WARP_LOOP(i, n) {
-		if (i >= n) continue;
-		float2 a = make_float2(0.0f, 0.0f);
-		if (i >= accFrom) {
-			a = acc[i];
-			acc[i] = make_float2(0.0f, 0.0f);
+	const uint32_t nPairs = (n + 1u) >> 1, T = gridDim.x * blockDim.x;
+	for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < nPairs; q0 += 2u * T) {
+		const uint32_t q1 = q0 + T;
+		const bool has1 = q1 < nPairs;
+		const bool both0 = 2u * q0 + 1u < n, both1 = has1 && 2u * q1 + 1u < n;
+		Pair2 v0 = load_pair(vel, q0, both0), v1 = {};
+		if (has1) v1 = load_pair(vel, q1, both1);
+		Pair2 a0 = {}, a1 = {}; // only particles added since the last step carry an acceleration (demo4.cpp:146)
+		if (2u * q0 + 1u >= accFrom) {
+			if (2u * q0 >= accFrom) { a0.a = acc[2u * q0]; acc[2u * q0] = make_float2(0.0f, 0.0f); }
+			if (both0) { a0.b = acc[2u * q0 + 1u]; acc[2u * q0 + 1u] = make_float2(0.0f, 0.0f); }
 		}
-		a.x = __fadd_rn(force.x, a.x); // operator+= evaluates b + a (vecmath.h:249-252)
-		a.y = __fadd_rn(force.y, a.y);
-		float2 v = vel[i];
-		v.x = __fadd_rn(__fmul_rn(a.x, dt), v.x);
-		v.y = __fadd_rn(__fmul_rn(a.y, dt), v.y);
-		vel[i] = v;
+		if (has1 && 2u * q1 + 1u >= accFrom) {
+			if (2u * q1 >= accFrom) { a1.a = acc[2u * q1]; acc[2u * q1] = make_float2(0.0f, 0.0f); }
+			if (both1) { a1.b = acc[2u * q1 + 1u]; acc[2u * q1 + 1u] = make_float2(0.0f, 0.0f); }
+		}
+		v0.a = integrate_one(v0.a, a0.a, force, dt);
+		v0.b = integrate_one(v0.b, a0.b, force, dt);
+		store_pair(vel, q0, both0, v0);
+		if (has1) {
+			v1.a = integrate_one(v1.a, a1.a, force, dt);
+			v1.b = integrate_one(v1.b, a1.b, force, dt);
+			store_pair(vel, q1, both1, v1);
+		}
 	}
 }
 
@@ -163,67 +206,85 @@ __device__ __forceinline__ uint32_t claim_cell_rank(uint32_t key, bool valid, ui
 	return base + (uint32_t)__popc(peers & ((1u << lane_id()) - 1u));
 }
 
+// one particle of predict_key_kernel: predict (demo4.cpp:330-339), then decide where it is filed / sent
+__device__ __forceinline__ void predict_file_one(const GridDesc &g, const StripDesc &sd, Counters *__restrict__ ctr, bool in, uint32_t i, uint32_t nSorted,
+                                                 float2 &p, float2 &q, float2 v, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellOld, float dt,
+                                                 int doPredict, uint32_t &key, uint32_t &packed) {
+	key = 0xFFFFFF00u | lane_id(); // unique per lane: never matches
+	packed = SPH_KEY_NONE;
+	if (!in) return;
+	if (doPredict) {
+		q = p; // prevPosition = curPosition
+		p.x = __fadd_rn(__fmul_rn(v.x, dt), p.x);
+		p.y = __fadd_rn(__fmul_rn(v.y, dt), p.y);
+	}
+	bool authoritative = true;
+	if (sd.world > 1 && i < nSorted) { // ghosts of the previous grid are not ours to file
+		const int rowOld = (int)(cellOld[i] >> 16);
+		authoritative = rowOld >= g.ownLo && rowOld < g.ownHi;
+	}
+	if (!authoritative) return;
+	int cx, cy;
+	cell_of(g, p, cx, cy);
+	bool placed = false;
+	if (cy >= g.rowLo && cy < g.rowHi) {
+		key = (uint32_t)(cy - g.rowLo) * (uint32_t)g.gx + (uint32_t)cx;
+		packed = pack_cell(cx, cy);
+		placed = true;
+	}
+	if (sd.world > 1) {
+		HaloRecord rec;
+		rec.pos = p;
+		rec.prev = q;
+		rec.id = id[i];
+		rec.pad = 0;
+		if (sd.rank > 0 && cy < g.ownLo + sd.halo) {
+			const uint32_t at = atomicAdd(&sd.sendDown->count, 1u);
+			if (at < sd.haloCap) halo_records(sd.sendDown)[at] = rec;
+			else atomicOr(&ctr->overflow, 2u);
+			placed = true;
+		}
+		if (sd.rank + 1 < sd.world && cy >= g.ownHi - sd.halo) {
+			const uint32_t at = atomicAdd(&sd.sendUp->count, 1u);
+			if (at < sd.haloCap) halo_records(sd.sendUp)[at] = rec;
+			else atomicOr(&ctr->overflow, 2u);
+			placed = true;
+		}
+	}
+	if (!placed) atomicAdd(&ctr->lost, 1u);
+}
+
+// A thread takes the particle pair (2q, 2q+1): one 16-byte access per float2 array (see integrate_kernel).
 __global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, StripDesc sd, Counters *__restrict__ ctr, float2 *__restrict__ pos,
                                                                  float2 *__restrict__ prev, const float2 *__restrict__ vel,
                                                                  const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellOld,
                                                                  uint32_t *__restrict__ cellNew, uint32_t *__restrict__ rank,
                                                                  uint32_t *__restrict__ cellCount, float dt, int doPredict) {
 	const uint32_t n = ctr->n, nSorted = ctr->nSorted;
-	SPH_WARP_LOOP(i, n) {
-		const bool in = i < n;
-		uint32_t key = 0xFFFFFF00u | lane_id(); // unique per lane: never matches
-		uint32_t packed = SPH_KEY_NONE;
-		if (in) {
-			float2 p = pos[i];
-			float2 q = prev[i];
-			if (doPredict) {
-				const float2 v = vel[i];
-				q = p;
-				prev[i] = p;
-				p.x = __fadd_rn(__fmul_rn(v.x, dt), p.x);
-				p.y = __fadd_rn(__fmul_rn(v.y, dt), p.y);
-				pos[i] = p;
-			}
-			bool authoritative = true;
-			if (sd.world > 1 && i < nSorted) { // ghosts of the previous grid are not ours to file
-				const int rowOld = (int)(cellOld[i] >> 16);
-				authoritative = rowOld >= g.ownLo && rowOld < g.ownHi;
-			}
-			if (authoritative) {
-				int cx, cy;
-				cell_of(g, p, cx, cy);
-				bool placed = false;
-				if (cy >= g.rowLo && cy < g.rowHi) {
-					key = (uint32_t)(cy - g.rowLo) * (uint32_t)g.gx + (uint32_t)cx;
-					packed = pack_cell(cx, cy);
-					placed = true;
-				}
-				if (sd.world > 1) {
-					HaloRecord rec;
-					rec.pos = p;
-					rec.prev = q;
-					rec.id = id[i];
-					rec.pad = 0;
-					if (sd.rank > 0 && cy < g.ownLo + sd.halo) {
-						const uint32_t at = atomicAdd(&sd.sendDown->count, 1u);
-						if (at < sd.haloCap) halo_records(sd.sendDown)[at] = rec;
-						else atomicOr(&ctr->overflow, 2u);
-						placed = true;
-					}
-					if (sd.rank + 1 < sd.world && cy >= g.ownHi - sd.halo) {
-						const uint32_t at = atomicAdd(&sd.sendUp->count, 1u);
-						if (at < sd.haloCap) halo_records(sd.sendUp)[at] = rec;
-						else atomicOr(&ctr->overflow, 2u);
-						placed = true;
-					}
-				}
-				if (!placed) atomicAdd(&ctr->lost, 1u);
-			}
+	const uint32_t nPairs = (n + 1u) >> 1;
+	SPH_WARP_LOOP(qi, nPairs) {
+		const bool in0 = 2u * qi < n, in1 = 2u * qi + 1u < n; // in1 implies in0
+		Pair2 p = {}, q = {}, v = {};
+		if (in0) {
+			p = load_pair(pos, qi, in1);
+			q = load_pair(prev, qi, in1);
+			if (doPredict) v = load_pair(vel, qi, in1);
 		}
-		const uint32_t r = claim_cell_rank(key, packed != SPH_KEY_NONE, cellCount);
-		if (in) {
-			cellNew[i] = packed;
-			rank[i] = r;
+		uint32_t key0, packed0, key1, packed1;
+		predict_file_one(g, sd, ctr, in0, 2u * qi, nSorted, p.a, q.a, v.a, id, cellOld, dt, doPredict, key0, packed0);
+		predict_file_one(g, sd, ctr, in1, 2u * qi + 1u, nSorted, p.b, q.b, v.b, id, cellOld, dt, doPredict, key1, packed1);
+		if (in0 && doPredict) {
+			store_pair(prev, qi, in1, q);
+			store_pair(pos, qi, in1, p);
+		}
+		const uint32_t r0 = claim_cell_rank(key0, packed0 != SPH_KEY_NONE, cellCount);
+		const uint32_t r1 = claim_cell_rank(key1, packed1 != SPH_KEY_NONE, cellCount);
+		if (in1) {
+			*reinterpret_cast<uint2 *>(cellNew + 2u * qi) = make_uint2(packed0, packed1);
+			*reinterpret_cast<uint2 *>(rank + 2u * qi) = make_uint2(r0, r1);
+		} else if (in0) {
+			cellNew[2u * qi] = packed0;
+			rank[2u * qi] = r0;
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctr->nIn = n;
@@ -1128,16 +1189,38 @@ __global__ void __launch_bounds__(SPH_THREADS) collide_velocity_kernel(Counters 
                                                                       float2 *__restrict__ vel, const DevBody *__restrict__ bodies, int nbodies,
                                                                       float invDt, int doCollide, int doVelocity, int commit) {
 	const uint32_t n = commit ? ctr->nOut : ctr->n;
-	SPH_WARP_LOOP(i, n) {
-		if (i >= n) continue;
-		float2 p = pos[i];
+	// particle pairs, two pairs in flight per thread (see integrate_kernel)
+	const uint32_t nPairs = (n + 1u) >> 1, T = gridDim.x * blockDim.x;
+	for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < nPairs; q0 += 2u * T) {
+		const uint32_t q1 = q0 + T;
+		const bool has1 = q1 < nPairs;
+		const bool both0 = 2u * q0 + 1u < n, both1 = has1 && 2u * q1 + 1u < n;
+		Pair2 p0 = load_pair(pos, q0, both0), p1 = {}, r0 = {}, r1 = {};
+		if (has1) p1 = load_pair(pos, q1, both1);
+		if (doVelocity) {
+			r0 = load_pair(prev, q0, both0);
+			if (has1) r1 = load_pair(prev, q1, both1);
+		}
 		if (doCollide) {
-			p = col::all(p, bodies, nbodies);
-			pos[i] = p;
+			p0.a = col::all(p0.a, bodies, nbodies);
+			if (both0) p0.b = col::all(p0.b, bodies, nbodies);
+			store_pair(pos, q0, both0, p0);
+			if (has1) {
+				p1.a = col::all(p1.a, bodies, nbodies);
+				if (both1) p1.b = col::all(p1.b, bodies, nbodies);
+				store_pair(pos, q1, both1, p1);
+			}
 		}
 		if (doVelocity) {
-			const float2 q = prev[i];
-			vel[i] = make_float2(__fmul_rn(__fsub_rn(p.x, q.x), invDt), __fmul_rn(__fsub_rn(p.y, q.y), invDt));
+			Pair2 v;
+			v.a = make_float2(__fmul_rn(__fsub_rn(p0.a.x, r0.a.x), invDt), __fmul_rn(__fsub_rn(p0.a.y, r0.a.y), invDt));
+			v.b = make_float2(__fmul_rn(__fsub_rn(p0.b.x, r0.b.x), invDt), __fmul_rn(__fsub_rn(p0.b.y, r0.b.y), invDt));
+			store_pair(vel, q0, both0, v);
+			if (has1) {
+				v.a = make_float2(__fmul_rn(__fsub_rn(p1.a.x, r1.a.x), invDt), __fmul_rn(__fsub_rn(p1.a.y, r1.a.y), invDt));
+				v.b = make_float2(__fmul_rn(__fsub_rn(p1.b.x, r1.b.x), invDt), __fmul_rn(__fsub_rn(p1.b.y, r1.b.y), invDt));
+				store_pair(vel, q1, both1, v);
+			}
 		}
 	}
 	// closes the step: every block read nOut above, nobody in this kernel reads n / nSorted

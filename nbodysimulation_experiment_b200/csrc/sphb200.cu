@@ -216,6 +216,8 @@ inline cudaError_t copy_strided(void *dst, size_t dstPitch, const void *src, siz
 	return cudaMemcpy2DAsync(dst, dstPitch, src, srcPitch, width, rows, kind, stream);
 }
 
+// (integrate / collide+velocity take two particle pairs per thread, predict+key one pair: they are launched with
+// blocks_for(n / 4) and blocks_for(n / 2))
 inline unsigned blocks_for(uint64_t n) {
 	uint64_t b = (n + SPH_THREADS - 1) / SPH_THREADS;
 	if (b < 1) b = 1;
@@ -419,7 +421,7 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	if (parts & GRID_FRONT) {
 		CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
 		if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
-		predict_key_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
+		predict_key_kernel<<<blocks_for((s->hostN + 1) / 2), SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
 		                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
 		if (timed) record_phase(s, PH_PREDICT + 1);
 	}
@@ -1185,7 +1187,7 @@ static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, f
 	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
 	if (parts & GRID_FRONT) {
 		record_phase(s, 0);
-		integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt); // also opens the step
+		integrate_kernel<<<blocks_for((s->hostN + 3) / 4), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt); // also opens the step
 		s->accFrom = 0xFFFFFFFFu;
 		record_phase(s, PH_INTEGRATE + 1);
 		run_viscosity(s, k, nb);
@@ -1199,7 +1201,7 @@ static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, f
 	record_phase(s, PH_DENSITY + 1);
 	run_delta(s, k, nb);
 	record_phase(s, PH_DELTA + 1);
-	collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1); // also closes the step
+	collide_velocity_kernel<<<blocks_for((s->hostN + 3) / 4), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), invDt, 1, 1, 1); // also closes the step
 	record_phase(s, PH_COLLIDE + 1);
 	return SPH_OK;
 }
@@ -1351,7 +1353,7 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 	switch (pass) {
 		case SPH_PASS_INTEGRATE: {
 			const float2 force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y);
-			integrate_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
+			integrate_kernel<<<blocks_for((s->hostN + 3) / 4), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->vel.in(), s->acc.in(), s->accFrom, force, dt);
 			s->accFrom = 0xFFFFFFFFu;
 		} break;
 		case SPH_PASS_VISCOSITY:
@@ -1379,10 +1381,10 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 			run_delta(s, k, nb);
 			break;
 		case SPH_PASS_COLLIDE:
-			collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), 1.0f / dt, 1, 0, 0);
+			collide_velocity_kernel<<<blocks_for((s->hostN + 3) / 4), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), 1.0f / dt, 1, 0, 0);
 			break;
 		case SPH_PASS_VELOCITY:
-			collide_velocity_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), 1.0f / dt, 0, 1, 0);
+			collide_velocity_kernel<<<blocks_for((s->hostN + 3) / 4), SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->dBodies, (int)s->bodies.size(), 1.0f / dt, 0, 1, 0);
 			break;
 		default: return fail(s, SPH_ERR_INVALID, "unknown pass %d", pass);
 	}
