@@ -485,11 +485,13 @@ def test_block_per_cell_and_warp_per_cell_sweeps_agree_with_the_oracle(pkg, scen
     cpu.close()
 
 
-@pytest.mark.parametrize("nx,spacing,g,steps", [(512, 0.1, -10.0, 60), (1024, 0.1, -0.5219, 24), (384, 0.05, -3.0, 16)])
+@pytest.mark.parametrize("nx,spacing,g,steps", [(512, 0.1, -10.0, 60), (1024, 0.1, -0.5219, 300), (384, 0.05, -3.0, 16)])
 def test_one_launch_flow_sweep_equals_nine_launch_sweep_at_scale(pkg, nx, spacing, g, steps):
     """The dependency-driven one-launch sweep (persistent warps, per-cell done flags) against the nine
     per-colour launches at sizes where every SM is busy and cells of different colours really run
-    concurrently: 262 144 particles in a violent collapse (g = -10), the 1M bench scene, a dense block.
+    concurrently: 262 144 particles in a violent collapse (g = -10), the 1M bench scene for the length of the bench
+    run (late in it heavy cells keep their neighbours waiting, profiles/r1_final_kernels_dambreak1m_step260.txt), a
+    dense block.
     Bit-identical state, and two flow runs agree with each other (no ordering left to chance)."""
     from nbodysimulation_experiment_b200 import scenes
 
