@@ -284,15 +284,25 @@ def run_ours(args):
         kernel_name = {"viscosity": f"{sweep_kernel}<{fpn}, 1>" if swept else f"viscosity_kernel<{fpn}>", "delta": f"{sweep_kernel}<{fpn}, 0>" if swept else f"delta_kernel<{fpn}>",
                        "density": "density_kernel<Exact>", "reorder": "reorder_kernel", "predict_key": "predict_key_kernel",
                        "collide_velocity": "collide_velocity_kernel"}.get(dom, dom)
-        traffic = None
+        traffic, issue = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_final_traffic.json" if one_launch else "r1_traffic.json")
         if os.path.exists(tpath) and args.workload == "dambreak_1m" and world == 1 and args.fp == "exact":
-            traffic = json.load(open(tpath)).get(kernel_name, {}).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath)).get(kernel_name, {})
+            traffic = prof.get("dram_bytes_per_launch")
+            if prof.get("warp_instructions_per_launch") and launch_ms > 0 and clocks.get("sm_mhz"):
+                # what actually binds the kernel: warp instructions per launch (ncu, same scene at step 2-3) over the launch
+                # time measured here, against the issue rate of the chip (148 SMs x 4 schedulers x 1 instruction per clock)
+                peak_ginst = 148 * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+                ach_ginst = prof["warp_instructions_per_launch"] / (launch_ms * 1e-3) / 1e9
+                issue = {"bound": "instruction issue", "achieved": ach_ginst, "peak": peak_ginst, "unit": "G warp-instructions/s", "frac": ach_ginst / peak_ginst,
+                         "warp_instructions_per_launch": prof["warp_instructions_per_launch"], "ncu_issue_slots_busy_pct": prof.get("issue_slots_busy_pct"),
+                         "source": "profiles/r1_final_traffic.json (ncu --set full of this kernel) + kernel_ms measured in this run"}
         roofline = {
             "bound": "hbm", "kernel": kernel_name + ((" (the whole %s sweep, nine colours in one launch)" if one_launch else " (one of the 9 colour launches of the %s sweep)") % dom if swept else ""),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": launch_ms,
             "step_model": {"bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world)},
+            "issue": issue,
             "note": ("the pair passes are instruction-issue bound, not HBM bound: 90 % of the issue slots busy in this kernel, DRAM idle "
                      "(profiles/r1_final_kernels_dambreak1m.txt); " if one_launch else
                      "the pair passes are instruction-issue bound, not HBM bound: 73 % of the issue slots busy in this kernel, DRAM idle (profiles/r1_kernels_dambreak1m.txt); ")

@@ -108,11 +108,16 @@ def traffic(src, dst, what):
             b += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
         i = hdr.index("gpu__time_duration.sum")
         t = float(r[i].replace(",", "")) * tscale.get(units[i], 1.0)
-        a = agg.setdefault(name, [0, 0.0, 0.0])
+        inst = float(r[hdr.index("smsp__inst_executed.sum")].replace(",", "")) if "smsp__inst_executed.sum" in hdr else 0.0
+        busy = float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")].replace(",", "")) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in hdr else 0.0
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0, 0.0])
         a[0] += 1
         a[1] += b
         a[2] += t
-    out = {k: {"launches_captured": c, "dram_bytes_per_launch": b / c, "duration_us_per_launch": t / c} for k, (c, b, t) in agg.items()}
+        a[3] += inst
+        a[4] += busy
+    out = {k: {"launches_captured": c, "dram_bytes_per_launch": b / c, "duration_us_per_launch": t / c, "warp_instructions_per_launch": i / c,
+               "issue_slots_busy_pct": u / c} for k, (c, b, t, i, u) in agg.items()}
     out["_source"] = what
     json.dump(out, open(dst, "w"), indent=1)
 
