@@ -169,6 +169,8 @@ def run_ours(args):
         if world > 1:
             sim.comm_init(uid[which])
             sim.set_strip(*scenes.block_strips(sim, world)[rank])
+            if args.rebalance:
+                sim.set_rebalance(args.rebalance)
         return scenes.fill_block(sim)
 
     def all_max(x):
@@ -317,7 +319,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {nx}x{nx} = {n_total} particles on {world} GPU(s), spacing {spacing}, h = cell = 0.3, dt = 1/60, "
-                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}, sweep {args.sweep}",
+                                   f"grid {gx}x{gy}, gravity {gravity[1]:.4f}, fp_mode {args.fp}, solver {args.solver}, sweep {args.sweep}" + (f", strips re-balanced every {args.rebalance} steps" if (args.rebalance and world > 1) else ""),
                        "particles": n_total, "particles_rank0": n_local, "cells": cells,
                        "candidates_per_particle_rank0": stats.pair_candidates / max(n_local, 1),
                        "l2": "state streamed once per phase (>130 MB/step) and a 256 MiB L2 flush before the timed region",
@@ -442,6 +444,7 @@ def main():
     ap.add_argument("--sweep", default="auto", choices=["auto", "flow", "warp", "team"],
                     help="coloured sweep kernel: one launch with dependency flags (flow), nine launches warp-per-cell (warp) or block-per-cell (team)")
     ap.add_argument("--halo-rows", type=int, default=0)
+    ap.add_argument("--rebalance", type=int, default=0, help="strips: re-balance every N steps by the particles per grid row (0 = static split)")
     ap.add_argument("--no-clock-sampler", action="store_true", help="experiment: do not poll NVML during the timed region")
     ap.add_argument("--nx-total", type=int, default=0, help="edge of the whole block, overriding the weak-scaling rule")
     ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")

@@ -214,6 +214,16 @@ int sph_comm_init(SphHandle h, const uint8_t id128[128]);
 /* rows [row_begin, row_end) of the grid this rank owns (even split of occupied rows at init) */
 int sph_set_strip(SphHandle h, int32_t row_begin, int32_t row_end);
 int sph_get_strip(SphHandle h, int32_t *row_begin, int32_t *row_end);
+/* Periodic re-balancing (off by default): every `every_steps` steps the ranks all-reduce the particles
+ * per grid row, plan the same new split (prefix over the histogram, each boundary moving at most `max_shift_rows`
+ * rows, 0 = 2) and the rows that change hands travel with that step's neighbour exchange.  Call before adding
+ * particles: the cell arrays are re-sized for the whole grid so that a strip can move without reallocating.
+ * Results stay bit-identical to one GPU.  every_steps = 0 switches it off. */
+int sph_set_rebalance(SphHandle h, int32_t every_steps, int32_t max_shift_rows);
+/* The planner on its own (host arithmetic, no device): row_counts[grid_y], old_bounds[world + 1] (= 0, B_1, ...,
+ * grid_y) -> new_bounds[world + 1].  Exposed for tests and for hosts that want to inspect the split. */
+int sph_plan_strip_bounds(const uint32_t *row_counts, int32_t grid_y, const int32_t *old_bounds, int32_t world, int32_t halo_rows,
+                          int32_t max_shift_rows, int32_t *new_bounds);
 /* The particles this rank owns, compacted in arbitrary order: creation ids, ParticleData records
  * (as sph_read_particles), and/or Render()'s positions and colours.  Any output pointer may be NULL;
  * *count receives the number of owned particles.  Works for world_size = 1 too. */

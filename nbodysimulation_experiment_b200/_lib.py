@@ -121,6 +121,8 @@ SIGNATURES = {
     "sph_comm_init": (C.c_int, [c_vp, c_vp]),
     "sph_set_strip": (C.c_int, [c_vp, c_i32, c_i32]),
     "sph_get_strip": (C.c_int, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "sph_set_rebalance": (C.c_int, [c_vp, C.c_int32, C.c_int32]),
+    "sph_plan_strip_bounds": (C.c_int, [c_vp, C.c_int32, c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp]),
     "sph_read_owned": (C.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_sz, c_vp, c_sz, C.POINTER(c_u64)]),
     "sph_render_owned": (C.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp, c_sz]),
     "sph_wait_render_owned": (C.c_int, [c_vp, C.POINTER(c_u64)]),

@@ -194,6 +194,10 @@ struct StripDesc {
 	int32_t rank, world, halo;  // halo rows on each side
 	uint32_t haloCap;           // records per HaloBuffer
 	HaloBuffer *sendDown, *sendUp;
+	// Rows this rank owned when the PREVIOUS grid was built: what it is authoritative for.  Equal to GridDesc's
+	// ownLo/ownHi except in the one step that re-balances the strips: there the particles are kept / sent by the
+	// new rows (GridDesc) while authority still follows the old ones (sph_set_rebalance).
+	int32_t authLo, authHi;
 };
 
 // shared tail of predict_key / unpack: claim a rank inside the cell, one atomic per distinct cell per warp
@@ -221,7 +225,7 @@ __device__ __forceinline__ void predict_file_one(const GridDesc &g, const StripD
 	bool authoritative = true;
 	if (sd.world > 1 && i < nSorted) { // ghosts of the previous grid are not ours to file
 		const int rowOld = (int)(cellOld[i] >> 16);
-		authoritative = rowOld >= g.ownLo && rowOld < g.ownHi;
+		authoritative = rowOld >= sd.authLo && rowOld < sd.authHi;
 	}
 	if (!authoritative) return;
 	int cx, cy;
@@ -327,6 +331,18 @@ __global__ void __launch_bounds__(SPH_THREADS) unpack_kernel(GridDesc g, Counter
 		const uint32_t end = min(first + count, capacity);
 		atomicMax(&ctr->nIn, end);
 	}
+}
+
+// Particles per grid row of the rows this rank owns (read off the previous grid's prefix), written at the row's GLOBAL
+// index, and the rank's first row at out[gy + rank]: summed over the ranks (all-reduce) every rank sees the whole
+// histogram and all boundaries, and plans the same new split (plan_strip_bounds).
+__global__ void row_counts_kernel(GridDesc g, const uint32_t *__restrict__ cellStart, uint32_t *__restrict__ out, int rank) {
+	const int r = g.ownLo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (r < g.ownHi) {
+		const uint32_t local = (uint32_t)(r - g.rowLo);
+		out[r] = cellStart[(local + 1u) * (uint32_t)g.gx] - cellStart[local * (uint32_t)g.gx];
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) out[g.gy + rank] = (uint32_t)g.ownLo;
 }
 
 __global__ void reset_halo_kernel(HaloBuffer *a, HaloBuffer *b) {

@@ -87,6 +87,7 @@ NcclApi g_nccl;
 constexpr int kNcclUint8 = 1;  // ncclUint8, nccl.h:279
 constexpr int kNcclUint32 = 3; // ncclUint32, nccl.h:281
 constexpr int kNcclMax = 2;    // ncclMax, nccl.h:262
+constexpr int kNcclSum = 0;    // ncclSum, nccl.h:260
 constexpr int kHaloResizeEvery = 16; // steps between re-sizings of the exchange messages
 
 enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DENSITY, PH_DELTA, PH_COLLIDE, PH_EXCHANGE, PH_COUNT };
@@ -156,6 +157,14 @@ struct SphSim {
 	uint64_t exchanges = 0;
 	NcclComm comm = nullptr;
 	uint32_t *dOwnedCount = nullptr, *dOwnedIds = nullptr;
+	// periodic re-balancing of the strips (sph_set_rebalance)
+	int rebalanceEvery = 0, rebalanceMaxShift = 2;
+	bool allocFullGrid = false;         // cell arrays sized for any window of the grid, so a strip can move without reallocating
+	uint32_t *dRowCounts = nullptr;     // gy row counts + world first-rows, all-reduced
+	std::vector<uint32_t> hRowCounts;
+	bool pendingRetarget = false;       // apply pendLo/pendHi between the viscosity pass and the grid build of this step
+	int pendLo = 0, pendHi = 0;
+	uint64_t rebalances = 0;
 	// overlapped strip readback (sph_render_owned / sph_wait_render_owned)
 	uint32_t *hOwnedCount = nullptr; // pinned
 	uint64_t ownedShipped = 0, ownedLast = 0;
@@ -423,6 +432,9 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 		if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
 		predict_key_kernel<<<blocks_for((s->hostN + 1) / 2), SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
 		                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
+		// from the next grid on, authority follows the rows this grid is built for
+		s->strip.authLo = g.ownLo;
+		s->strip.authHi = g.ownHi;
 		if (timed) record_phase(s, PH_PREDICT + 1);
 	}
 	if ((parts & GRID_EXCHANGE) && s->strip.world > 1) {
@@ -563,6 +575,11 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	g.rowHi = world > 1 ? std::min(g.gy, ownHi + halo) : g.gy;
 	if (world == 1 && (ownLo != 0 || ownHi != g.gy)) return fail(s, SPH_ERR_INVALID, "a single-GPU simulation owns the whole grid");
 	g.nCells = (uint32_t)(g.rowHi - g.rowLo) * (uint32_t)g.gx;
+	s->strip.authLo = ownLo;
+	s->strip.authHi = ownHi;
+	// everything sized by the window of rows: for the window itself, or (re-balancing on) for the whole grid
+	const int allocRows = s->allocFullGrid ? g.gy : (g.rowHi - g.rowLo);
+	const size_t allocCells = (size_t)allocRows * (size_t)g.gx;
 	cudaFree(s->cellCount);
 	cudaFree(s->cellStart);
 	cudaFree(s->tileSums);
@@ -571,19 +588,99 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	cudaFree(s->rowColor);
 	s->cellCount = s->cellStart = s->tileSums = s->colorList = s->sweepFlow = s->rowColor = nullptr;
 	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
-	CU(s, cudaMalloc(&s->cellCount, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->cellStart, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CU(s, cudaMemset(s->cellStart, 0, ((size_t)g.nCells + 1) * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->tileSums, (size_t)s->nTiles * sizeof(uint32_t)));
-	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((g.rowHi - g.rowLo + 2) / 3 + 1);
+	CU(s, cudaMalloc(&s->cellCount, (allocCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->cellStart, (allocCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMemset(s->cellStart, 0, (allocCells + 1) * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->tileSums, ((allocCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE + 1) * sizeof(uint32_t)));
+	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((allocRows + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->sweepFlow, ((size_t)g.nCells + 2 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
-	CU(s, cudaMemset(s->sweepFlow, 0xFF, ((size_t)g.nCells + 2 + 65536) * sizeof(uint32_t))); // no grid yet: every cell empty
+	CU(s, cudaMalloc(&s->sweepFlow, (allocCells + 2 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
+	CU(s, cudaMemset(s->sweepFlow, 0xFF, (allocCells + 2 + 65536) * sizeof(uint32_t))); // no grid yet: every cell empty
 	CU(s, cudaMemset(s->sweepFlow, 0, 2 * sizeof(uint32_t)));
 	if (s->colorCount) CU(s, cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
 	s->flowEpoch = 0;
-	CU(s, cudaMalloc(&s->rowColor, (size_t)(g.rowHi - g.rowLo) * 3 * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->rowColor, (size_t)allocRows * 3 * sizeof(uint32_t)));
 	return SPH_OK;
+}
+
+// ---- periodic re-balancing of the strips ----------------------------------------------------------
+// New boundaries from the global row histogram: boundary r goes where the prefix of the counts reaches r/world of the
+// total, but (a) moves at most maxShift rows per re-balance, (b) stays `halo` rows inside the OLD ranges of the two
+// ranks it separates - every row of a rank's new window then belongs (old ownership) to the rank itself or to a direct
+// neighbour, so one neighbour exchange moves everything - and (c) leaves every strip at least minRows tall.  Pure
+// integer arithmetic on data every rank holds identically: all ranks plan the same split.  strips.plan_bounds (Python)
+// is the same function, tested on the CPU.
+std::vector<int> plan_strip_bounds(const uint32_t *rowCounts, int gy, const std::vector<int> &oldB, int halo, int maxShift) {
+	const int world = (int)oldB.size() - 1;
+	const int minRows = 2 * halo + 4;
+	uint64_t total = 0;
+	for (int r = 0; r < gy; ++r) total += rowCounts[r];
+	std::vector<int> nb = oldB;
+	if (total == 0) return nb;
+	uint64_t prefix = 0;
+	int row = 0;
+	for (int b = 1; b < world; ++b) {
+		const uint64_t target = total * (uint64_t)b / (uint64_t)world;
+		while (row < gy && prefix < target) prefix += rowCounts[row++]; // smallest `row` with sum(rows < row) >= target
+		int want = row;
+		want = std::max(want, oldB[b] - maxShift);
+		want = std::min(want, oldB[b] + maxShift);
+		want = std::max(want, oldB[b - 1] + halo);
+		want = std::min(want, oldB[b + 1] - halo);
+		nb[b] = want;
+	}
+	for (int b = 1; b < world; ++b) nb[b] = std::max(nb[b], nb[b - 1] + minRows);
+	for (int b = world - 1; b >= 1; --b) nb[b] = std::min(nb[b], nb[b + 1] - minRows);
+	for (int b = 1; b <= world; ++b)
+		if (nb[b] - nb[b - 1] < minRows) return oldB; // the grid is too short for this many strips: leave it alone
+	return nb;
+}
+
+// Called at the top of a step that is due: histogram of the owned rows, one all-reduce, the plan.  Sets
+// pendingRetarget (the same on every rank) and this rank's new rows.
+int plan_rebalance(SphSim *s) {
+	const GridDesc &g = s->grid;
+	const int world = s->strip.world, rank = s->strip.rank;
+	NcclApi &nc = g_nccl;
+	const size_t words = (size_t)g.gy + (size_t)world;
+	if (!s->dRowCounts) CU(s, cudaMalloc(&s->dRowCounts, words * sizeof(uint32_t)));
+	s->hRowCounts.resize(words);
+	CU(s, cudaMemsetAsync(s->dRowCounts, 0, words * sizeof(uint32_t), s->stream));
+	const int rows = g.ownHi - g.ownLo;
+	row_counts_kernel<<<(rows + 255) / 256, 256, 0, s->stream>>>(g, s->cellStart, s->dRowCounts, rank);
+	CU(s, cudaGetLastError());
+	const int rca = nc.AllReduce(s->dRowCounts, s->dRowCounts, words, kNcclUint32, kNcclSum, s->comm, s->stream);
+	if (rca != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce (row histogram) failed: %s", nc.GetErrorString(rca));
+	CU(s, cudaMemcpyAsync(s->hRowCounts.data(), s->dRowCounts, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+	CU(s, cudaStreamSynchronize(s->stream));
+	std::vector<int> oldB(world + 1);
+	for (int r = 0; r < world; ++r) oldB[r] = (int)s->hRowCounts[(size_t)g.gy + r];
+	oldB[world] = g.gy;
+	const std::vector<int> nb = plan_strip_bounds(s->hRowCounts.data(), g.gy, oldB, s->strip.halo, s->rebalanceMaxShift);
+	s->pendingRetarget = nb != oldB;
+	s->pendLo = nb[rank];
+	s->pendHi = nb[rank + 1];
+	return SPH_OK;
+}
+
+// Between the viscosity pass (previous grid, old rows) and the grid build of the same step: the rank's rows and its
+// window change; nothing is copied or reallocated (the cell arrays were sized for the whole grid).  predict_key_kernel
+// then keeps / sends by the new rows while authority still follows the old ones (StripDesc::authLo/authHi), and the one
+// neighbour exchange of the step carries the particles whose rows changed hands together with the usual halo.
+void apply_retarget(SphSim *s) {
+	GridDesc &g = s->grid;
+	const int halo = s->strip.halo;
+	g.ownLo = s->pendLo;
+	g.ownHi = s->pendHi;
+	g.rowLo = std::max(0, g.ownLo - halo);
+	g.rowHi = std::min(g.gy, g.ownHi + halo);
+	g.nCells = (uint32_t)(g.rowHi - g.rowLo) * (uint32_t)g.gx;
+	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
+	for (StepGraph &c : s->graphs) cudaGraphExecDestroy(c.exec); // the grid description is baked into every launch
+	s->graphs.clear();
+	s->haloMsgRecords = s->strip.haloCap; // this exchange also carries the rows that change hands: ship whole buffers once
+	s->pendingRetarget = false;
+	s->rebalances++;
 }
 
 int run_delta(SphSim *s, const PairParams &k, unsigned nb) {
@@ -822,6 +919,7 @@ int sph_destroy(SphHandle s) {
 		if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (s->hCtrLag) cudaFreeHost(s->hCtrLag);
 	if (s->hOwnedCount) cudaFreeHost(s->hOwnedCount);
+	cudaFree(s->dRowCounts);
 	if (s->lagEvent) cudaEventDestroy(s->lagEvent);
 	for (auto &e : s->phaseEv)
 		if (e) cudaEventDestroy(e);
@@ -1192,6 +1290,7 @@ static int enqueue_step(SphSim *s, float dt, const PairParams &k, unsigned nb, f
 		record_phase(s, PH_INTEGRATE + 1);
 		run_viscosity(s, k, nb);
 		record_phase(s, PH_VISCOSITY + 1);
+		if (s->pendingRetarget) apply_retarget(s); // (never inside a graph capture: a step that re-balances is not graphable)
 	}
 	int rc = launch_grid_build(s, dt, true, false, true, parts);
 	if (rc != SPH_OK) return rc;
@@ -1254,7 +1353,11 @@ int sph_step(SphHandle s, float dt) {
 		rc = maybe_resize_halo(s);
 		if (rc != SPH_OK) return rc;
 	}
-	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2;
+	if (s->cfg.world_size > 1 && s->rebalanceEvery > 0 && s->steppedOnce && s->steps % (uint64_t)s->rebalanceEvery == 0) {
+		rc = plan_rebalance(s);
+		if (rc != SPH_OK) return rc;
+	}
+	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2 && !s->pendingRetarget;
 	// One GPU: the whole step is one graph.  Strips: NCCL send/recv inside a captured stream dead-locked on
 	// this stack (NCCL 2.28.9, driver 580), so the launches before and after the exchange are two graphs
 	// and the exchange itself is enqueued plainly between them.
@@ -1708,6 +1811,33 @@ int sph_wait_render_owned(SphHandle s, uint64_t *count) {
 	s->ownedLast = std::max<uint64_t>(n, 1);
 	s->ownedPending = false;
 	if (count) *count = n;
+	return SPH_OK;
+}
+
+int sph_plan_strip_bounds(const uint32_t *rowCounts, int32_t gridY, const int32_t *oldBounds, int32_t world, int32_t haloRows, int32_t maxShiftRows,
+                          int32_t *newBounds) {
+	if (!rowCounts || !oldBounds || !newBounds || gridY <= 0 || world <= 0) return SPH_ERR_INVALID;
+	const std::vector<int> oldB(oldBounds, oldBounds + world + 1);
+	const std::vector<int> nb = plan_strip_bounds(rowCounts, gridY, oldB, haloRows, maxShiftRows > 0 ? maxShiftRows : 2);
+	for (int b = 0; b <= world; ++b) newBounds[b] = nb[b];
+	return SPH_OK;
+}
+
+int sph_set_rebalance(SphHandle s, int32_t everySteps, int32_t maxShiftRows) {
+	CHECK_HANDLE(s);
+	if (everySteps < 0 || maxShiftRows < 0) return fail(s, SPH_ERR_INVALID, "negative argument");
+	if (s->cfg.world_size == 1 || everySteps == 0) {
+		s->rebalanceEvery = 0;
+		return SPH_OK;
+	}
+	if (s->nextId != 0 && !s->allocFullGrid) return fail(s, SPH_ERR_STATE, "enable re-balancing before adding particles (the cell arrays are re-sized)");
+	s->rebalanceEvery = everySteps;
+	s->rebalanceMaxShift = maxShiftRows > 0 ? maxShiftRows : 2;
+	if (!s->allocFullGrid) {
+		s->allocFullGrid = true;
+		CU(s, cudaStreamSynchronize(s->stream));
+		return configure_strip(s, s->grid.ownLo, s->grid.ownHi);
+	}
 	return SPH_OK;
 }
 

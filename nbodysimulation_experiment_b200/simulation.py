@@ -220,6 +220,10 @@ class ParticleSimulation:
     def set_strip(self, row_begin, row_end):
         self._check(self._lib.sph_set_strip(self._h, row_begin, row_end))
 
+    def set_rebalance(self, every_steps, max_shift_rows=2):
+        """Re-balance the strips every `every_steps` steps (0 = off); call before adding particles."""
+        self._check(self._lib.sph_set_rebalance(self._h, int(every_steps), int(max_shift_rows)))
+
     def get_strip(self):
         a, b = C.c_int32(), C.c_int32()
         self._check(self._lib.sph_get_strip(self._h, C.byref(a), C.byref(b)))

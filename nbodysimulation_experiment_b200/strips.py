@@ -70,3 +70,39 @@ def halo_capacity_estimate(n_per_rank, rows_per_rank, halo, safety=3.0):
     strip's mean density, times a safety factor for compression during the run."""
     per_row = n_per_rank / max(rows_per_rank, 1)
     return int(per_row * halo * safety) + 4096
+
+
+def plan_bounds(row_counts, old_bounds, halo, max_shift=2):
+    """New strip boundaries from the global row histogram - the host mirror of plan_strip_bounds in
+    csrc/sphb200.cu, same integer arithmetic.  old_bounds = [B_0 = 0, B_1, ..., B_world = grid_y]; rank r owns rows
+    [B_r, B_r+1).  Boundary r goes where the prefix of the counts reaches r/world of the total, but moves at most
+    max_shift rows, stays `halo` rows inside the old ranges of the two ranks it separates (every row of a rank's new
+    window then belongs to the rank itself or to a direct neighbour: one neighbour exchange moves everything) and
+    leaves every strip at least 2*halo + 4 rows tall.  Returns the old bounds when that cannot be met."""
+    counts = [int(c) for c in row_counts]
+    old = [int(b) for b in old_bounds]
+    world, gy = len(old) - 1, len(counts)
+    min_rows = 2 * halo + 4
+    total = sum(counts)
+    nb = list(old)
+    if total == 0:
+        return nb
+    prefix, row = 0, 0
+    for b in range(1, world):
+        target = total * b // world
+        while row < gy and prefix < target:
+            prefix += counts[row]
+            row += 1
+        want = row
+        want = max(want, old[b] - max_shift)
+        want = min(want, old[b] + max_shift)
+        want = max(want, old[b - 1] + halo)
+        want = min(want, old[b + 1] - halo)
+        nb[b] = want
+    for b in range(1, world):
+        nb[b] = max(nb[b], nb[b - 1] + min_rows)
+    for b in range(world - 1, 0, -1):
+        nb[b] = min(nb[b], nb[b + 1] - min_rows)
+    if any(nb[b] - nb[b - 1] < min_rows for b in range(1, world + 1)):
+        return old
+    return nb

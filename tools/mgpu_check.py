@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--solver", default="gs")
     ap.add_argument("--halo-rows", type=int, default=0)
+    ap.add_argument("--rebalance", type=int, default=0, help="re-balance the strips every N steps (0 = static strips)")
+    ap.add_argument("--max-shift", type=int, default=2)
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -43,6 +45,8 @@ def main():
     sim.comm_init(uid[0])
     strips = scenes.block_strips(sim, world)
     sim.set_strip(*strips[rank])
+    if a.rebalance:
+        sim.set_rebalance(a.rebalance, a.max_shift)
     scenes.fill_block(sim)
     n_total = a.nx * a.nx
     counts = [None] * world
@@ -57,6 +61,7 @@ def main():
             sim.Update(dt)
         mine = sim.read_owned(records=True)
         sim.GetStats()  # raises on overflow flags
+        final_strip = sim.get_strip()
     except Exception as e:  # fail fast on every rank instead of hanging the others in a collective
         err = repr(e)
     flag = torch.tensor([0 if err is None else 1], device="cuda")
@@ -66,6 +71,10 @@ def main():
         os._exit(2)
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine["ids"], mine["records"]))
+    final = [None] * world
+    dist.all_gather_object(final, final_strip)
+    if rank == 0:
+        print("strips after", a.steps, "steps:", final, flush=True)
     ok = True
     if rank == 0:
         ids = np.concatenate([g[0] for g in gathered])
