@@ -36,10 +36,11 @@ def main():
     solver = SPH_SOLVER_GATHER if a.solver == "gather" else SPH_SOLVER_COLORED_GS
     dt = float(np.float32(1.0) / np.float32(60.0))
 
-    # every strip is given room for the whole scene (particles and exchange records): under g = -10 the column falls
-    # into the bottom strips, and the default sizing (3x the even share) overflows from 4 strips on
+    # every strip is given room for the whole scene twice over (what it holds + what arrives behind it in one step) and
+    # for whole-scene exchange messages: under g = -10 the column falls into the bottom strips, and the default sizing
+    # (3x the even share) overflows from 4 strips on
     sim = scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, a.gravity), device=local, rank=rank, world_size=world, solver=solver,
-                             halo_rows=a.halo_rows, capacity=a.nx * a.nx + 1024, halo_capacity=a.nx * a.nx)
+                             halo_rows=a.halo_rows, capacity=2 * a.nx * a.nx + 1024, halo_capacity=a.nx * a.nx)
     uid = [ParticleSimulation.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim.comm_init(uid[0])
