@@ -555,6 +555,7 @@ def test_two_gpu_strips_match_one_gpu_bitwise():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
-                          os.path.join(root, "tools", "mgpu_check.py"), "--nx", "256", "--steps", "40"], capture_output=True, text=True, timeout=240)
-    assert out.returncode == 0 and "MGPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    for port, extra in (("29517", []), ("29518", ["--rebalance", "8", "--steps", "100"])):  # static strips, then re-balanced every 8 steps
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", port,
+                              os.path.join(root, "tools", "mgpu_check.py"), "--nx", "256", "--steps", "40"] + extra, capture_output=True, text=True, timeout=240)
+        assert out.returncode == 0 and "MGPU PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
