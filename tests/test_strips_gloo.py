@@ -130,3 +130,69 @@ def test_cell_rows_matches_reference_dump():
     # after put_particles the reference re-filed the grid from the final positions
     last = g[f"state{int(g['steps'][-1])}"]
     assert np.array_equal(strips.cell_rows(last[:, 1], HALF_H, CELL, GRID_Y), g["refiled_cell_of_particle"][:, 1])
+
+
+# ---- a re-balancing step (sph_set_rebalance) over gloo ---------------------------------------------
+RB_GRID_Y, RB_HALO, RB_N = 120, 3, 30000
+
+
+def rebalance_state():
+    """particles piled up near the floor (rows on the previous grid), each moving at most one row in this step"""
+    rng = np.random.default_rng(21)
+    before = np.minimum(rng.geometric(0.06, RB_N) - 1, RB_GRID_Y - 1)
+    after = np.clip(before + rng.integers(-1, 2, RB_N), 0, RB_GRID_Y - 1)
+    return before, after
+
+
+def rebalance_worker(rank, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    before, after = rebalance_state()
+    ids = np.arange(RB_N)
+    old = [0, 60, RB_GRID_Y]
+    # what the device does: row counts of the rows I own at their global index + my first row, summed over the ranks
+    words = torch.zeros(RB_GRID_Y + WORLD, dtype=torch.int64)
+    mine = strips.owned(before, (old[rank], old[rank + 1]))
+    words[:RB_GRID_Y] = torch.from_numpy(np.bincount(before[mine], minlength=RB_GRID_Y))
+    words[RB_GRID_Y + rank] = old[rank]
+    dist.all_reduce(words)
+    assert words[:RB_GRID_Y].sum().item() == RB_N and words[RB_GRID_Y:].tolist() == old[:WORLD]
+    new = strips.plan_bounds(words[:RB_GRID_Y].tolist(), words[RB_GRID_Y:].tolist() + [RB_GRID_Y], RB_HALO, max_shift=4)
+    plans = [None] * WORLD
+    dist.all_gather_object(plans, new)
+    assert all(p == new for p in plans), plans  # every rank planned the same split
+    assert new[1] == old[1] - 4  # the pile is near the floor: the boundary moves down as far as it may
+    own = (new[rank], new[rank + 1])
+    keep, down, up, lost = strips.classify(after[mine], rank, WORLD, own, RB_HALO, RB_GRID_Y)  # authority: old rows; keep / send: new rows
+    assert not lost.any()
+    my_ids = ids[mine]
+    recv = []
+    for peer, mask in ((rank - 1, down), (rank + 1, up)):
+        if not 0 <= peer < WORLD:
+            continue
+        send_buf = torch.from_numpy(my_ids[mask].astype(np.int64))
+        cnt, other = torch.tensor([len(send_buf)]), torch.zeros(1, dtype=torch.long)
+        for r in [dist.isend(cnt, peer), dist.irecv(other, peer)]:
+            r.wait()
+        got = torch.zeros(int(other.item()), dtype=torch.int64)
+        for r in [dist.isend(send_buf, peer), dist.irecv(got, peer)]:
+            r.wait()
+        recv.append(got.numpy())
+    arrived = np.concatenate(recv) if recv else np.zeros(0, np.int64)
+    wlo, whi = strips.window(own, RB_HALO, RB_GRID_Y, WORLD)
+    arrived = arrived[(after[arrived] >= wlo) & (after[arrived] < whi)]  # unpack_kernel files only what is inside the window
+    local = np.concatenate([my_ids[keep], arrived])
+    assert len(np.unique(local)) == len(local)
+    assert np.array_equal(np.sort(local), ids[(after >= wlo) & (after < whi)])  # the whole new window
+    np.save(os.path.join(out_dir, f"rb_ids{rank}.npy"), local[strips.owned(after[local], own)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_rebalancing_step(tmp_path):
+    """Histogram all-reduce, identical plans, authority by the old rows and keep/send by the new ones, one exchange:
+    afterwards ownership is a partition and every rank holds its whole new window."""
+    port = free_port()
+    mp.spawn(rebalance_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    owned = np.concatenate([np.load(tmp_path / f"rb_ids{r}.npy") for r in range(WORLD)])
+    assert len(owned) == RB_N and len(np.unique(owned)) == RB_N
