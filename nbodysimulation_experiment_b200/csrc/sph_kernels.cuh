@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(SPH_THREADS) delta_kernel(GridDesc g, PairPara
 // order is what keeps the double-density relaxation stable (each pair sees the displacements of
 // the pairs before it); a plain gather of all pair terms from the old state overshoots and blows
 // up on stiff scenes ("why not Jacobi").  Cells whose (cx mod 3, cy mod 3) agree have
-// disjoint 3x3 footprints, so the nine colours are swept one launch after another; inside a
+// disjoint 3x3 footprints, so the nine colours are swept in order (nine launches, or one launch with per-cell dependency flags: color_sweep_flow_kernel); inside a
 // launch ONE WARP owns one cell, walks its particles by ascending id, and spreads each particle's
 // candidate loop over its 32 lanes (candidate k belongs to lane k mod 32 for the whole sweep, so a
 // staged candidate is only ever written by one lane).  The partner is updated at once, the

@@ -1345,7 +1345,7 @@ int sph_step(SphHandle s, float dt) {
 	const float invDt = 1.0f / dt; // demo4.cpp:287
 	const float2 force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y); // gravity + externalForce, :306
 
-	// Steady state (nothing appended since the last step, no per-phase timing): the ~27
+	// Steady state (nothing appended since the last step, no per-phase timing): the ~14
 	// launches of a step are replayed from a CUDA graph, which removes the launch gaps that dominate
 	// small scenes.  Kernel arguments depend on which half of each double buffer is current, so graphs
 	// are cached per buffer parity, staging capacity, dt, force and parameters.
