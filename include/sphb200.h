@@ -61,8 +61,11 @@ enum {
 	SPH_FLAG_NO_GRAPHS = 1u << 1,    /* launch every kernel of a step individually instead of replaying a CUDA graph */
 	SPH_FLAG_SWEEP_TEAM = 1u << 2,   /* coloured sweeps: always one thread block per cell (default: chosen by particle count) */
 	SPH_FLAG_SWEEP_WARP = 1u << 3,   /* coloured sweeps: nine launches, one warp per cell */
-	SPH_FLAG_SWEEP_FLOW = 1u << 4    /* coloured sweeps: one launch for all colours, persistent warps + per-cell dependency flags
+	SPH_FLAG_SWEEP_FLOW = 1u << 4,   /* coloured sweeps: one launch for all colours, persistent warps + per-cell dependency flags
 	                                    (default for >= 131072 particles); all three kernels give identical bits */
+	SPH_FLAG_EXCHANGE_NCCL = 1u << 5 /* strips: ship the halo records as ncclSend/ncclRecv messages instead of storing them straight
+	                                    into the neighbour's memory (the fallback sph_comm_init picks by itself when CUDA IPC or peer
+	                                    access is not available) */
 };
 
 /* Runtime replacement for the compile-time world of sph.h:18-72. */
@@ -211,6 +214,18 @@ int sph_get_phase_ms(SphHandle h, float out[SPH_NUM_PHASES], uint64_t *steps);
  * host uses torch.distributed), every rank then calls sph_comm_init before adding particles. */
 int sph_comm_unique_id(uint8_t id128[128]);
 int sph_comm_init(SphHandle h, const uint8_t id128[128]);
+/* sph_comm_init also maps the two neighbours' halo mailboxes into this process (CUDA IPC): from then on
+ * predict_key_kernel stores a strip's migrating and halo particles straight into the neighbour's HBM over NVLink, a
+ * device-side sequence number tells the neighbour when they are complete, and a step is one CUDA graph with no host
+ * or NCCL call inside.  All NCCL connections are opened here, so the first sph_step costs what every step costs
+ * (the reference's contract: every Update is one frame, app.cpp:228-236).
+ *
+ * The same for strips that all live in THIS process - one host thread driving several GPUs like the reference's
+ * single-threaded app loop would, or several strips on one GPU (tests): create the handles with rank = 0..n-1,
+ * world_size = n, wire them with sph_comm_init_local and step them together with sph_step_group (sph_step refuses
+ * such a handle: the group call enqueues every strip's sends before any strip's wait). */
+int sph_comm_init_local(SphHandle *handles, int32_t n);
+int sph_step_group(SphHandle *handles, int32_t n, float dt);
 /* rows [row_begin, row_end) of the grid this rank owns (even split of occupied rows at init) */
 int sph_set_strip(SphHandle h, int32_t row_begin, int32_t row_end);
 int sph_get_strip(SphHandle h, int32_t *row_begin, int32_t *row_end);

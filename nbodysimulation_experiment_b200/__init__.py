@@ -8,9 +8,9 @@ from . import _lib
 from ._lib import (SPH_FLAG_PHASE_TIMING, SPH_FP_EXACT, SPH_FP_FAST, SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER, SphConfig,
                    SphParams, SphStats)
 from .scenes import block_scene, bodies_scene
-from .simulation import ParticleSimulation, SphError, pinned_empty
+from .simulation import ParticleSimulation, SphError, StripGroup, bind_host_to_gpu, pinned_empty
 
 __all__ = [
-    "ParticleSimulation", "SphError", "SphConfig", "SphParams", "SphStats", "pinned_empty",
+    "ParticleSimulation", "StripGroup", "bind_host_to_gpu", "SphError", "SphConfig", "SphParams", "SphStats", "pinned_empty",
     "SPH_FP_EXACT", "SPH_FP_FAST", "SPH_FLAG_PHASE_TIMING", "SPH_SOLVER_COLORED_GS", "SPH_SOLVER_GATHER", "block_scene", "bodies_scene",
 ]

@@ -21,6 +21,7 @@ SPH_FLAG_NO_GRAPHS = 2
 SPH_FLAG_SWEEP_TEAM = 4
 SPH_FLAG_SWEEP_WARP = 8
 SPH_FLAG_SWEEP_FLOW = 16
+SPH_FLAG_EXCHANGE_NCCL = 32
 SPH_SOLVER_COLORED_GS = 0
 SPH_SOLVER_GATHER = 1
 SPH_NUM_PHASES = 9
@@ -119,6 +120,8 @@ SIGNATURES = {
     "sph_get_phase_ms": (C.c_int, [c_vp, C.POINTER(c_f * SPH_NUM_PHASES), C.POINTER(c_u64)]),
     "sph_comm_unique_id": (C.c_int, [c_vp]),
     "sph_comm_init": (C.c_int, [c_vp, c_vp]),
+    "sph_comm_init_local": (C.c_int, [C.POINTER(c_vp), c_i32]),
+    "sph_step_group": (C.c_int, [C.POINTER(c_vp), c_i32, c_f]),
     "sph_set_strip": (C.c_int, [c_vp, c_i32, c_i32]),
     "sph_get_strip": (C.c_int, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32)]),
     "sph_set_rebalance": (C.c_int, [c_vp, C.c_int32, C.c_int32]),

@@ -29,9 +29,10 @@ struct Counters {
 	uint32_t nSorted;  // particles covered by cellStart / cellOf (the previous step's grid)
 	uint32_t nIn;      // n + particles received from neighbour strips this step
 	uint32_t nOut;     // particles kept by this step's grid build (= cellStart[nCells])
-	uint32_t reserved0, reserved1;
+	uint32_t xseq;     // strip exchanges published so far (the mailbox protocol's sequence number, see publish_halo_kernel)
+	uint32_t reserved1;
 	uint32_t lost;     // particles that left the local rows with nowhere to go
-	uint32_t overflow; // capacity overflow flags
+	uint32_t overflow; // capacity overflow flags: 1 particles, 2 halo buffer, 4 sweep queue, 8 neighbour strip did not publish in time
 	uint32_t minNbr, maxNbr, minCell, maxCell;
 	unsigned long long pairCandidates;
 };
@@ -183,8 +184,16 @@ struct HaloRecord { // what a neighbour needs to file a particle into this step'
 	float2 pos, prev;
 	uint32_t id, pad;
 };
+// A mailbox: header + records.  Every rank holds four of them (from the lower / upper neighbour, two exchange
+// parities); the SENDER fills them: predict_key_kernel stores the records straight into the neighbour's mailbox (peer
+// memory over NVLink, mapped with CUDA IPC or - several strips in one process - plain device pointers), and
+// publish_halo_kernel then writes the count and, with release semantics at system scope, the exchange's sequence
+// number.  The receiver polls `seq` (wait_halo_kernel) and files the records (unpack_kernel).  No host in the loop, no
+// fixed message size, and the whole step stays one CUDA graph.  Two parities because a sender may run one exchange
+// ahead: it writes box e+1 while the receiver still reads box e; it cannot reach e+2 before it has seen the receiver's
+// own e+1, which the receiver publishes after it has unpacked e (stream order).
 struct HaloBuffer {
-	uint32_t count, pad[7]; // 32-byte header
+	uint32_t count, seq, pad[6]; // 32-byte header
 	// HaloRecord records[capacity] follow
 };
 __device__ __forceinline__ HaloRecord *halo_records(HaloBuffer *b) { return reinterpret_cast<HaloRecord *>(b + 1); }
@@ -193,7 +202,10 @@ __device__ __forceinline__ const HaloRecord *halo_records(const HaloBuffer *b) {
 struct StripDesc {
 	int32_t rank, world, halo;  // halo rows on each side
 	uint32_t haloCap;           // records per HaloBuffer
-	HaloBuffer *sendDown, *sendUp;
+	// where the records for the lower / upper neighbour go, by exchange parity: the neighbour's mailbox (peer memory)
+	// or, with the NCCL transport, a local send buffer of the same layout
+	HaloBuffer *outDown[2], *outUp[2];
+	uint32_t *sendCount;        // [0] records packed for the lower neighbour in this exchange, [1] for the upper, [2] peak since the last look
 	// Rows this rank owned when the PREVIOUS grid was built: what it is authoritative for.  Equal to GridDesc's
 	// ownLo/ownHi except in the one step that re-balances the strips: there the particles are kept / sent by the
 	// new rows (GridDesc) while authority still follows the old ones (sph_set_rebalance).
@@ -211,11 +223,13 @@ __device__ __forceinline__ uint32_t claim_cell_rank(uint32_t key, bool valid, ui
 }
 
 // one particle of predict_key_kernel: predict (demo4.cpp:330-339), then decide where it is filed / sent
+// (toDown / toUp: a copy goes to that neighbour's mailbox; every lane of the warp returns, the caller ships warp-wide)
 __device__ __forceinline__ void predict_file_one(const GridDesc &g, const StripDesc &sd, Counters *__restrict__ ctr, bool in, uint32_t i, uint32_t nSorted,
-                                                 float2 &p, float2 &q, float2 v, const uint32_t *__restrict__ id, const uint32_t *__restrict__ cellOld, float dt,
-                                                 int doPredict, uint32_t &key, uint32_t &packed) {
+                                                 float2 &p, float2 &q, float2 v, const uint32_t *__restrict__ cellOld, float dt,
+                                                 int doPredict, uint32_t &key, uint32_t &packed, bool &toDown, bool &toUp) {
 	key = 0xFFFFFF00u | lane_id(); // unique per lane: never matches
 	packed = SPH_KEY_NONE;
+	toDown = toUp = false;
 	if (!in) return;
 	if (doPredict) {
 		q = p; // prevPosition = curPosition
@@ -237,25 +251,34 @@ __device__ __forceinline__ void predict_file_one(const GridDesc &g, const StripD
 		placed = true;
 	}
 	if (sd.world > 1) {
-		HaloRecord rec;
-		rec.pos = p;
-		rec.prev = q;
-		rec.id = id[i];
-		rec.pad = 0;
-		if (sd.rank > 0 && cy < g.ownLo + sd.halo) {
-			const uint32_t at = atomicAdd(&sd.sendDown->count, 1u);
-			if (at < sd.haloCap) halo_records(sd.sendDown)[at] = rec;
-			else atomicOr(&ctr->overflow, 2u);
-			placed = true;
-		}
-		if (sd.rank + 1 < sd.world && cy >= g.ownHi - sd.halo) {
-			const uint32_t at = atomicAdd(&sd.sendUp->count, 1u);
-			if (at < sd.haloCap) halo_records(sd.sendUp)[at] = rec;
-			else atomicOr(&ctr->overflow, 2u);
-			placed = true;
-		}
+		toDown = sd.rank > 0 && cy < g.ownLo + sd.halo;
+		toUp = sd.rank + 1 < sd.world && cy >= g.ownHi - sd.halo;
+		placed = placed || toDown || toUp;
 	}
 	if (!placed) atomicAdd(&ctr->lost, 1u);
+}
+
+// Warp-wide: the lanes with `want` claim consecutive slots of the exchange's out-box (one atomic per warp on the LOCAL
+// counter) and store their records there - for a peer mailbox these are posted writes over NVLink, 24 contiguous
+// bytes per lane.  Slots past the capacity are dropped; publish_halo_kernel reports them.
+__device__ __forceinline__ void ship_records(bool want, HaloBuffer *box, uint32_t *counter, uint32_t cap, float2 p, float2 q, uint32_t id) {
+	const uint32_t mask = __ballot_sync(0xffffffffu, want);
+	if (!mask) return;
+	const int leader = __ffs(mask) - 1;
+	uint32_t base = 0;
+	if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (want) {
+		const uint32_t at = base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
+		if (at < cap) {
+			HaloRecord rec;
+			rec.pos = p;
+			rec.prev = q;
+			rec.id = id;
+			rec.pad = 0;
+			halo_records(box)[at] = rec;
+		}
+	}
 }
 
 // A thread takes the particle pair (2q, 2q+1): one 16-byte access per float2 array (see integrate_kernel).
@@ -266,6 +289,9 @@ __global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, St
                                                                  uint32_t *__restrict__ cellCount, float dt, int doPredict) {
 	const uint32_t n = ctr->n, nSorted = ctr->nSorted;
 	const uint32_t nPairs = (n + 1u) >> 1;
+	// this exchange's number is xseq + 1 (publish_halo_kernel, which runs after this kernel, makes it current)
+	const uint32_t par = sd.world > 1 ? ((ctr->xseq + 1u) & 1u) : 0u;
+	HaloBuffer *const boxDown = sd.outDown[par], *const boxUp = sd.outUp[par];
 	SPH_WARP_LOOP(qi, nPairs) {
 		const bool in0 = 2u * qi < n, in1 = 2u * qi + 1u < n; // in1 implies in0
 		Pair2 p = {}, q = {}, v = {};
@@ -275,11 +301,19 @@ __global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, St
 			if (doPredict) v = load_pair(vel, qi, in1);
 		}
 		uint32_t key0, packed0, key1, packed1;
-		predict_file_one(g, sd, ctr, in0, 2u * qi, nSorted, p.a, q.a, v.a, id, cellOld, dt, doPredict, key0, packed0);
-		predict_file_one(g, sd, ctr, in1, 2u * qi + 1u, nSorted, p.b, q.b, v.b, id, cellOld, dt, doPredict, key1, packed1);
+		bool down0, up0, down1, up1;
+		predict_file_one(g, sd, ctr, in0, 2u * qi, nSorted, p.a, q.a, v.a, cellOld, dt, doPredict, key0, packed0, down0, up0);
+		predict_file_one(g, sd, ctr, in1, 2u * qi + 1u, nSorted, p.b, q.b, v.b, cellOld, dt, doPredict, key1, packed1, down1, up1);
 		if (in0 && doPredict) {
 			store_pair(prev, qi, in1, q);
 			store_pair(pos, qi, in1, p);
+		}
+		if (sd.world > 1 && __any_sync(0xffffffffu, down0 || up0 || down1 || up1)) {
+			const uint32_t id0 = (down0 || up0) ? id[2u * qi] : 0u, id1 = (down1 || up1) ? id[2u * qi + 1u] : 0u;
+			ship_records(down0, boxDown, sd.sendCount + 0, sd.haloCap, p.a, q.a, id0);
+			ship_records(down1, boxDown, sd.sendCount + 0, sd.haloCap, p.b, q.b, id1);
+			ship_records(up0, boxUp, sd.sendCount + 1, sd.haloCap, p.a, q.a, id0);
+			ship_records(up1, boxUp, sd.sendCount + 1, sd.haloCap, p.b, q.b, id1);
 		}
 		const uint32_t r0 = claim_cell_rank(key0, packed0 != SPH_KEY_NONE, cellCount);
 		const uint32_t r1 = claim_cell_rank(key1, packed1 != SPH_KEY_NONE, cellCount);
@@ -294,15 +328,75 @@ __global__ void __launch_bounds__(SPH_THREADS) predict_key_kernel(GridDesc g, St
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctr->nIn = n;
 }
 
-// append the records received from one neighbour behind the local particles and file them
-__global__ void __launch_bounds__(SPH_THREADS) unpack_kernel(GridDesc g, Counters *__restrict__ ctr, const HaloBuffer *__restrict__ in, uint32_t haloCap,
-                                                            uint32_t capacity, uint32_t baseOffset, const HaloBuffer *__restrict__ before,
+// ---- the strip exchange: publish, wait, unpack ------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+// Runs after predict_key_kernel (all records of this exchange are stored): writes the counts into the out-boxes and
+// then, released at system scope, the exchange number - the receiver's cue.  Resets the local slot counters for the
+// next exchange and makes the exchange current (ctr->xseq).  One thread.
+__global__ void publish_halo_kernel(StripDesc sd, Counters *__restrict__ ctr) {
+	const uint32_t e = ctr->xseq + 1u, par = e & 1u;
+	HaloBuffer *box[2] = { sd.outDown[par], sd.outUp[par] };
+	uint32_t most = 0;
+#pragma unroll
+	for (int d = 0; d < 2; ++d) {
+		const uint32_t c = sd.sendCount[d];
+		sd.sendCount[d] = 0u;
+		if (!box[d]) continue;
+		if (c > sd.haloCap) atomicOr(&ctr->overflow, 2u);
+		most = max(most, c);
+		box[d]->count = min(c, sd.haloCap);
+	}
+	if (most > sd.sendCount[2]) sd.sendCount[2] = most;
+	__threadfence_system(); // the records (previous kernel) and the counts before the sequence numbers
+#pragma unroll
+	for (int d = 0; d < 2; ++d)
+		if (box[d]) st_release_sys(&box[d]->seq, e);
+	ctr->xseq = e;
+}
+
+// Lane 0 waits for the lower neighbour's mailbox of the current exchange, lane 1 for the upper one.  A neighbour that
+// does not publish within `timeoutNs` (it died, or its host stopped stepping) must not hang this GPU: the wait gives
+// up, raises overflow bit 8 - sph_get_stats turns it into SPH_ERR_COMM - and later waits return at once.
+__global__ void wait_halo_kernel(Counters *__restrict__ ctr, const HaloBuffer *down0, const HaloBuffer *down1, const HaloBuffer *up0, const HaloBuffer *up1,
+                                 unsigned long long timeoutNs) {
+	const uint32_t e = ctr->xseq, par = e & 1u;
+	const HaloBuffer *box = threadIdx.x == 0 ? (par ? down1 : down0) : (threadIdx.x == 1 ? (par ? up1 : up0) : nullptr);
+	if (!box || (ctr->overflow & 8u)) return;
+	const unsigned long long t0 = global_timer_ns();
+	// sequence numbers only grow; (int) difference so that a wrap after 2^32 exchanges stays harmless
+	while ((int32_t)(ld_acquire_sys(&box->seq) - e) < 0) {
+		__nanosleep(200);
+		if (global_timer_ns() - t0 > timeoutNs) {
+			atomicOr(&ctr->overflow, 8u);
+			break;
+		}
+	}
+}
+
+// append the records received from one neighbour behind the local particles and file them; the mailbox is the one of
+// the current exchange's parity, `before` (same parity) is the neighbour unpacked ahead of this one
+__global__ void __launch_bounds__(SPH_THREADS) unpack_kernel(GridDesc g, Counters *__restrict__ ctr, const HaloBuffer *in0, const HaloBuffer *in1, uint32_t haloCap,
+                                                            uint32_t capacity, const HaloBuffer *before0, const HaloBuffer *before1,
                                                             float2 *__restrict__ pos, float2 *__restrict__ prev, uint32_t *__restrict__ id,
                                                             uint32_t *__restrict__ cellNew, uint32_t *__restrict__ rank, uint32_t *__restrict__ cellCount) {
+	const uint32_t e = ctr->xseq, par = e & 1u;
+	const HaloBuffer *in = par ? in1 : in0, *before = par ? before1 : before0;
+	if ((int32_t)(in->seq - e) < 0) return; // the wait timed out: nothing arrived (already reported)
 	// records land at [n + (count of the buffer unpacked before this one), ...)
 	if (blockIdx.x == 0 && threadIdx.x == 0 && in->count > haloCap) atomicOr(&ctr->overflow, 2u); // the sender packed more than a message ships
 	const uint32_t count = min(in->count, haloCap);
-	const uint32_t first = ctr->n + baseOffset + (before ? min(before->count, haloCap) : 0u);
+	const uint32_t first = ctr->n + ((before && (int32_t)(before->seq - e) >= 0) ? min(before->count, haloCap) : 0u);
 	SPH_WARP_LOOP(k, count) {
 		const bool ok = k < count && first + k < capacity;
 		uint32_t key = 0xFFFFFF00u | lane_id();
@@ -343,11 +437,6 @@ __global__ void row_counts_kernel(GridDesc g, const uint32_t *__restrict__ cellS
 		out[r] = cellStart[(local + 1u) * (uint32_t)g.gx] - cellStart[local * (uint32_t)g.gx];
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) out[g.gy + rank] = (uint32_t)g.ownLo;
-}
-
-__global__ void reset_halo_kernel(HaloBuffer *a, HaloBuffer *b) {
-	if (a) a->count = 0;
-	if (b) b->count = 0;
 }
 
 // ---- phase 4b: exclusive scan of the cell histogram ----------------------------------------

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,7 @@ struct NcclApi {
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
 	std::string error;
 	bool load() {
 		if (lib) return true;
@@ -79,6 +81,7 @@ struct NcclApi {
 		BIND(GroupStart, "ncclGroupStart")
 		BIND(GroupEnd, "ncclGroupEnd")
 		BIND(AllReduce, "ncclAllReduce")
+		BIND(AllGather, "ncclAllGather")
 #undef BIND
 		return true;
 	}
@@ -88,19 +91,31 @@ constexpr int kNcclUint8 = 1;  // ncclUint8, nccl.h:279
 constexpr int kNcclUint32 = 3; // ncclUint32, nccl.h:281
 constexpr int kNcclMax = 2;    // ncclMax, nccl.h:262
 constexpr int kNcclSum = 0;    // ncclSum, nccl.h:260
-constexpr int kHaloResizeEvery = 16; // steps between re-sizings of the exchange messages
+constexpr int kNcclMin = 3;    // ncclMin, nccl.h:263
+constexpr int kHaloResizeEvery = 16; // NCCL transport only: steps between re-sizings of the exchange messages
+constexpr unsigned long long kHaloWaitTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull; // a neighbour strip that is 20 s late is gone
+
+// How the records packed by predict_key_kernel reach the neighbour strips.
+enum Transport {
+	TR_NONE = 0,
+	TR_PEER,  // stored straight into the neighbour's mailboxes (CUDA IPC mapping of its memory, NVLink): the default
+	TR_LOCAL, // the same with plain pointers: all strips live in this process (sph_comm_init_local / sph_step_group)
+	TR_NCCL   // packed into local send buffers, shipped as fixed-size ncclSend/ncclRecv messages (fallback, SPH_FLAG_EXCHANGE_NCCL)
+};
 
 enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DENSITY, PH_DELTA, PH_COLLIDE, PH_EXCHANGE, PH_COUNT };
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
 struct StepGraphKey {
 	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, parts, flowEpoch;
+	uint32_t gridGen; // bumped whenever the grid description or the cell arrays change (configure_strip, apply_retarget)
 	float2 force;
 	PairParams k;
 };
 struct StepGraph {
 	StepGraphKey key;
 	uint32_t parityAfter = 0, flowEpochAfter = 0;
+	uint32_t exchanges = 0; // strip exchanges the graph publishes (0 or 1)
 	cudaGraphExec_t exec = nullptr;
 };
 
@@ -150,11 +165,19 @@ struct SphSim {
 
 	// y-strip decomposition
 	StripDesc strip = {};
-	HaloBuffer *sendBuf[2] = { nullptr, nullptr }, *recvBuf[2] = { nullptr, nullptr }; // [0] = lower neighbour, [1] = upper
-	size_t haloBytes = 0;        // allocation per buffer
-	uint32_t haloMsgRecords = 0; // records actually shipped per message (all ranks agree; re-sized every kHaloResizeEvery steps)
-	uint32_t *dPeak = nullptr;   // [0] peak records packed since the last re-size, [1] all-reduced maximum
-	uint64_t exchanges = 0;
+	int transport = TR_NONE;
+	unsigned char *mail = nullptr;     // the four mailboxes [from the lower | upper neighbour][exchange parity]: ONE allocation, the unit CUDA IPC exports
+	HaloBuffer *mailIn[2][2] = {};
+	unsigned char *sendMem = nullptr;  // NCCL transport only: four local send buffers [to the lower | upper neighbour][parity]
+	void *peerBase[2] = { nullptr, nullptr }; // CUDA IPC mappings of the neighbours' `mail` (TR_PEER)
+	size_t haloBytes = 0;        // bytes per mailbox: header + haloCap records, rounded to 256
+	uint32_t haloMsgRecords = 0; // NCCL transport: records shipped per message (all ranks agree; re-sized every kHaloResizeEvery steps)
+	uint32_t *dSendCount = nullptr; // [0],[1] slot counters of the current exchange (StripDesc::sendCount), [2] peak count, [3] all-reduced peak
+	uint64_t exchanges = 0;      // host mirror of Counters::xseq
+	uint32_t *hPeak = nullptr;   // pinned; NCCL transport: all-reduced peak record count, fetched asynchronously
+	cudaEvent_t peakEvent = nullptr;
+	bool peakPending = false;
+	std::vector<SphSim *> group; // TR_LOCAL: all strips of the simulation, in rank order (sph_step_group)
 	NcclComm comm = nullptr;
 	uint32_t *dOwnedCount = nullptr, *dOwnedIds = nullptr;
 	// periodic re-balancing of the strips (sph_set_rebalance)
@@ -183,12 +206,22 @@ struct SphSim {
 	cudaEvent_t phaseEv[PH_COUNT + 1] = {};
 	double phaseMs[PH_COUNT] = {};
 	uint64_t phaseSteps = 0;
-	float hostEmitterMs = 0.0f;
+	float hostEmitterMs = 0.0f; // host time of UpdateEmitter (demo4.cpp:296-299), summed since sph_reset_stats
+	uint64_t hostEmitterSteps = 0;
 	cudaEvent_t marks[8] = {};
 
 	// step graphs
 	bool useGraphs = true;
 	std::vector<StepGraph> graphs;
+	uint32_t gridGen = 0;
+
+	// launch configuration of the sweep kernels on THIS handle's device, per (fp mode, pass)
+	struct SweepLaunch {
+		bool ready = false;
+		int flowBlocksPerSM[97] = {};
+	} sweepLaunch[2][2];
+	int numSMs = 148;
+	size_t maxDynSmem = 200 * 1024;
 
 	std::string err;
 };
@@ -216,6 +249,24 @@ int fail(SphSim *s, int code, const char *fmt, ...) {
 	do {                                                  \
 		if (!(h)) return fail(nullptr, SPH_ERR_INVALID, "null handle"); \
 	} while (0)
+
+// Every entry point works on the handle's own device, whatever the caller's current device is, and puts the
+// caller's device back on return (two handles on different GPUs may live in one process).
+struct DeviceScope {
+	int prev = -1;
+	bool changed = false;
+	explicit DeviceScope(const SphSim *s) {
+		if (cudaGetDevice(&prev) == cudaSuccess && prev != s->cfg.device) changed = cudaSetDevice(s->cfg.device) == cudaSuccess;
+	}
+	~DeviceScope() {
+		if (changed) cudaSetDevice(prev);
+	}
+	DeviceScope(const DeviceScope &) = delete;
+	DeviceScope &operator=(const DeviceScope &) = delete;
+};
+#define ENTER(h)     \
+	CHECK_HANDLE(h); \
+	DeviceScope deviceScope__(h)
 
 // strided host<->device copy; the contiguous case must not go through cudaMemcpy2D (a million 8-byte
 // rows copy an order of magnitude slower than one flat transfer)
@@ -305,12 +356,6 @@ __global__ void set_counts_kernel(Counters *ctr, uint32_t n, uint32_t nSorted) {
 	ctr->nIn = n;
 	ctr->nOut = nSorted;
 }
-// records packed this step vs the records a message ships: remember the peak, flag what does not fit
-__global__ void note_peak_kernel(const HaloBuffer *down, const HaloBuffer *up, uint32_t *peak, uint32_t msgRecords, Counters *ctr) {
-	const uint32_t most = max(down ? down->count : 0u, up ? up->count : 0u);
-	if (most > peak[0]) peak[0] = most;
-	if (most > msgRecords) atomicOr(&ctr->overflow, 2u);
-}
 __global__ void grow_count_kernel(Counters *ctr, uint32_t n) {
 	ctr->n = n;
 	ctr->nIn = n;
@@ -367,81 +412,115 @@ void record_phase(SphSim *s, int idx) {
 }
 
 // ---- the grid build shared by sph_step and sph_run_pass(GRID) ------------------------------
-// Message size: NCCL needs it on the host, the record counts only exist on the device.  All ranks
-// therefore ship the same fixed number of records per message, re-agreed every kHaloResizeEvery steps
-// as 1.5 x the largest count any rank packed since (one stream sync + a 4-byte all-reduce).  The
-// first messages carry the whole buffer.  A count above the agreed size raises the overflow flag on
-// the sender (note_peak_kernel) and on the receiver (header count > records shipped).
+// NCCL transport only.  Message size: NCCL needs it on the host, the record counts only exist on the device.  All
+// ranks therefore ship the same fixed number of records per message, re-agreed every kHaloResizeEvery steps as
+// 1.5 x the largest count any rank packed since.  The decision is taken WITHOUT stalling the step: the all-reduce and
+// the copy of its result are enqueued behind step k, and the new size is applied at the first later step that finds
+// the copy complete.  A count above the agreed size raises the overflow flag on the receiver (header count > records
+// shipped).  (The peer transport has no message size: records are stored straight into the neighbour's mailbox.)
 int maybe_resize_halo(SphSim *s) {
 	const StripDesc &sd = s->strip;
+	if (s->transport != TR_NCCL) return SPH_OK;
 	NcclApi &nc = g_nccl;
-	if (s->exchanges > 0 && s->exchanges % kHaloResizeEvery == 0) {
-		int rca = nc.AllReduce(s->dPeak, s->dPeak + 1, 1, kNcclUint32, kNcclMax, s->comm, s->stream);
-		if (rca != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce failed: %s", nc.GetErrorString(rca));
-		uint32_t peak = 0;
-		CU(s, cudaMemcpyAsync(&peak, s->dPeak + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-		CU(s, cudaMemsetAsync(s->dPeak, 0, sizeof(uint32_t), s->stream));
-		CU(s, cudaStreamSynchronize(s->stream));
-		const uint64_t want = (uint64_t)peak + peak / 2 + 4096;
+	if (s->peakPending && s->exchanges % kHaloResizeEvery == 0) {
+		// every rank must switch at the same exchange: the result was requested 15 exchanges ago, so this wait is over
+		// before it starts (it is a wait, not a query, only to keep the ranks' decisions identical)
+		CU(s, cudaEventSynchronize(s->peakEvent));
+		const uint64_t peak = *s->hPeak, want = peak + peak / 2 + 4096;
 		s->haloMsgRecords = (uint32_t)std::min<uint64_t>(sd.haloCap, want);
+		s->peakPending = false;
 	}
-	s->exchanges++;
+	if (!s->peakPending && s->exchanges > 0 && s->exchanges % kHaloResizeEvery == 1) {
+		int rca = nc.AllReduce(s->dSendCount + 2, s->dSendCount + 3, 1, kNcclUint32, kNcclMax, s->comm, s->stream);
+		if (rca != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce failed: %s", nc.GetErrorString(rca));
+		CU(s, cudaMemcpyAsync(s->hPeak, s->dSendCount + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+		CU(s, cudaMemsetAsync(s->dSendCount + 2, 0, sizeof(uint32_t), s->stream));
+		CU(s, cudaEventRecord(s->peakEvent, s->stream));
+		s->peakPending = true;
+	}
 	return SPH_OK;
 }
 
-// migration + halo in one neighbour exchange (fixed-size messages, count in the header), then file
-// what arrived behind the local particles
-int exchange_halos(SphSim *s) {
+// Migration + halo in one neighbour exchange.  `front`: after predict_key_kernel has stored this rank's records into
+// the out-boxes, publish them (count, then the exchange number, released at system scope).  `back`: wait for the two
+// neighbours' boxes of the same exchange and file what arrived behind the local particles.  With the NCCL transport
+// the out-boxes are local and one grouped send/recv per neighbour moves them in between.
+int exchange_front(SphSim *s) {
+	publish_halo_kernel<<<1, 1, 0, s->stream>>>(s->strip, s->dCtr);
+	s->exchanges++;
+	CU(s, cudaGetLastError());
+	return SPH_OK;
+}
+int exchange_nccl(SphSim *s) {
 	const StripDesc &sd = s->strip;
 	if (!s->comm) return fail(s, SPH_ERR_STATE, "sph_comm_init was not called on this multi-GPU handle");
 	NcclApi &nc = g_nccl;
+	const int par = (int)(s->exchanges & 1u); // exchange_front made this exchange current
 	const size_t msgBytes = sizeof(HaloBuffer) + (size_t)s->haloMsgRecords * sizeof(HaloRecord);
-	note_peak_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1], s->dPeak, s->haloMsgRecords, s->dCtr);
 	int rc = nc.GroupStart();
 	if (rc == 0 && sd.rank > 0) {
-		rc = nc.Send(s->sendBuf[0], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
-		if (rc == 0) rc = nc.Recv(s->recvBuf[0], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+		rc = nc.Send(sd.outDown[par], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->mailIn[0][par], msgBytes, kNcclUint8, sd.rank - 1, s->comm, s->stream);
 	}
 	if (rc == 0 && sd.rank + 1 < sd.world) {
-		rc = nc.Send(s->sendBuf[1], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
-		if (rc == 0) rc = nc.Recv(s->recvBuf[1], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+		rc = nc.Send(sd.outUp[par], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(s->mailIn[1][par], msgBytes, kNcclUint8, sd.rank + 1, s->comm, s->stream);
 	}
 	const int rcEnd = nc.GroupEnd();
 	if (rc == 0) rc = rcEnd;
 	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL exchange failed: %s", nc.GetErrorString(rc));
-	const unsigned nb = blocks_for(s->haloMsgRecords);
+	return SPH_OK;
+}
+int exchange_back(SphSim *s) {
+	const StripDesc &sd = s->strip;
 	const GridDesc &g = s->grid;
-	if (sd.rank > 0)
-		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[0], s->haloMsgRecords, s->capacity, 0u, nullptr, s->pos.in(), s->prev.in(), s->id.in(),
-		                                                s->cellNew, s->rank, s->cellCount);
-	if (sd.rank + 1 < sd.world)
-		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->recvBuf[1], s->haloMsgRecords, s->capacity, 0u, sd.rank > 0 ? s->recvBuf[0] : nullptr, s->pos.in(),
-		                                                s->prev.in(), s->id.in(), s->cellNew, s->rank, s->cellCount);
+	const bool lower = sd.rank > 0, upper = sd.rank + 1 < sd.world;
+	wait_halo_kernel<<<1, 32, 0, s->stream>>>(s->dCtr, lower ? s->mailIn[0][0] : nullptr, lower ? s->mailIn[0][1] : nullptr, upper ? s->mailIn[1][0] : nullptr,
+	                                          upper ? s->mailIn[1][1] : nullptr, kHaloWaitTimeoutNs);
+	// the count lives in the mailbox: a fixed grid of grid-stride warps
+	const uint32_t shipCap = s->transport == TR_NCCL ? s->haloMsgRecords : sd.haloCap;
+	const unsigned nb = std::min(blocks_for(sd.haloCap), 148u * 4u);
+	if (lower)
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->mailIn[0][0], s->mailIn[0][1], shipCap, s->capacity, nullptr, nullptr, s->pos.in(), s->prev.in(),
+		                                                s->id.in(), s->cellNew, s->rank, s->cellCount);
+	if (upper)
+		unpack_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->mailIn[1][0], s->mailIn[1][1], shipCap, s->capacity, lower ? s->mailIn[0][0] : nullptr,
+		                                                lower ? s->mailIn[0][1] : nullptr, s->pos.in(), s->prev.in(), s->id.in(), s->cellNew, s->rank, s->cellCount);
 	CU(s, cudaGetLastError());
 	return SPH_OK;
 }
 
 enum { GRID_FRONT = 1, GRID_EXCHANGE = 2, GRID_BACK = 4, GRID_ALL = 7 };
-// parts: the strip exchange (NCCL) cannot be captured into a graph, so callers may enqueue the
-// launches before it and after it separately
+// parts: FRONT = up to and including the publication of this rank's halo records, BACK = from the wait for the
+// neighbours' records on.  The peer transport runs all of it as one graph; the NCCL transport enqueues its send/recv
+// (GRID_EXCHANGE, not capturable on this stack) between two graphs; strips of one process (sph_step_group) run every
+// strip's FRONT before any BACK, so that no kernel ever waits for work the host has not enqueued yet.
 int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed, int parts = GRID_ALL) {
 	const GridDesc &g = s->grid;
 	const unsigned nb = blocks_for(s->hostN);
 	if (parts & GRID_FRONT) {
+		if (s->strip.world > 1 && s->transport == TR_NONE) return fail(s, SPH_ERR_STATE, "sph_comm_init / sph_comm_init_local was not called on this multi-GPU handle");
 		CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
-		if (s->strip.world > 1) reset_halo_kernel<<<1, 1, 0, s->stream>>>(s->sendBuf[0], s->sendBuf[1]);
 		predict_key_kernel<<<blocks_for((s->hostN + 1) / 2), SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
 		                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
 		// from the next grid on, authority follows the rows this grid is built for
 		s->strip.authLo = g.ownLo;
 		s->strip.authHi = g.ownHi;
 		if (timed) record_phase(s, PH_PREDICT + 1);
+		if (s->strip.world > 1) {
+			int rc = exchange_front(s);
+			if (rc != SPH_OK) return rc;
+		}
 	}
-	if ((parts & GRID_EXCHANGE) && s->strip.world > 1) {
-		int rc = exchange_halos(s);
+	if ((parts & GRID_EXCHANGE) && s->strip.world > 1 && s->transport == TR_NCCL) {
+		int rc = exchange_nccl(s);
 		if (rc != SPH_OK) return rc;
 	}
 	if (!(parts & GRID_BACK)) return SPH_OK;
+	if (s->strip.world > 1) {
+		int rc = exchange_back(s);
+		if (rc != SPH_OK) return rc;
+	}
 	if (timed) record_phase(s, PH_EXCHANGE + 1);
 	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
 	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
@@ -487,28 +566,34 @@ void launch_density(SphSim *s, const PairParams &k, unsigned nb) {
 //   * color_sweep_kernel      - nine launches, one warp per cell (SPH_FLAG_SWEEP_WARP);
 //   * color_sweep_team_kernel - nine launches, one block per cell, for scenes whose colours have fewer cells than the
 //                               GPU has warp slots (the reference's own scenes).
+template <class M>
+constexpr int fp_index();
+template <>
+constexpr int fp_index<Exact>() { return 0; }
+template <>
+constexpr int fp_index<Fast>() { return 1; }
+
 template <class M, int PASS>
 void launch_sweeps(SphSim *s, const PairParams &k) {
-	static bool attrSet = false;
-	static int numSMs = 148;
-	static int flowBlocksPerSM[97] = {};
-	if (!attrSet) {
-		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	// per handle, not per process: function attributes and occupancy belong to the handle's device
+	SphSim::SweepLaunch &cfg = s->sweepLaunch[fp_index<M>()][PASS];
+	const int numSMs = s->numSMs;
+	int *flowBlocksPerSM = cfg.flowBlocksPerSM;
+	if (!cfg.ready) {
+		const int smem = (int)s->maxDynSmem;
+		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(color_sweep_team_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		// resident blocks per SM of the persistent kernel for every staging capacity (32..3072 in steps of 32), asked
 		// once here: the first steps of a simulation are never inside a graph capture
 		for (uint32_t c32 = 1; c32 <= 96; ++c32) {
 			int nbk = 0;
 			const size_t bytes = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(c32 * 32u, PASS);
-			if (bytes <= 200u * 1024u) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, color_sweep_flow_kernel<M, PASS>, SPH_FLOW_WARPS * 32, bytes);
+			if (bytes <= s->maxDynSmem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, color_sweep_flow_kernel<M, PASS>, SPH_FLOW_WARPS * 32, bytes);
 			flowBlocksPerSM[c32] = nbk;
 		}
 		cudaGetLastError();
-		attrSet = true;
+		cfg.ready = true;
 	}
 	// occupied cells of one colour <= min(cells of that colour, particles)
 	const uint64_t cells = std::min<uint64_t>(s->listStride, std::max<uint64_t>(s->hostN, 1));
@@ -580,6 +665,11 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	// everything sized by the window of rows: for the window itself, or (re-balancing on) for the whole grid
 	const int allocRows = s->allocFullGrid ? g.gy : (g.rowHi - g.rowLo);
 	const size_t allocCells = (size_t)allocRows * (size_t)g.gx;
+	// cached step graphs hold the old grid description and the pointers freed below
+	for (StepGraph &c : s->graphs)
+		if (c.exec) cudaGraphExecDestroy(c.exec);
+	s->graphs.clear();
+	s->gridGen++;
 	cudaFree(s->cellCount);
 	cudaFree(s->cellStart);
 	cudaFree(s->tileSums);
@@ -633,6 +723,11 @@ std::vector<int> plan_strip_bounds(const uint32_t *rowCounts, int gy, const std:
 	for (int b = world - 1; b >= 1; --b) nb[b] = std::min(nb[b], nb[b + 1] - minRows);
 	for (int b = 1; b <= world; ++b)
 		if (nb[b] - nb[b - 1] < minRows) return oldB; // the grid is too short for this many strips: leave it alone
+	// The two passes above may have pushed a boundary past what (a) and (b) allow (strips that START thinner than
+	// minRows): a boundary that jumps over rows of a non-neighbour would strand their particles.  Never trade a
+	// correct split for a better balanced one.
+	for (int b = 1; b < world; ++b)
+		if (std::abs(nb[b] - oldB[b]) > maxShift || nb[b] < oldB[b - 1] + halo || nb[b] > oldB[b + 1] - halo) return oldB;
 	return nb;
 }
 
@@ -663,6 +758,36 @@ int plan_rebalance(SphSim *s) {
 	return SPH_OK;
 }
 
+// The same plan for strips that live in one process (sph_comm_init_local): the histograms are summed on the host.
+int plan_rebalance_group(SphHandle *hs, int n) {
+	const int gy = hs[0]->grid.gy;
+	std::vector<uint32_t> total((size_t)gy, 0u);
+	std::vector<int> oldB((size_t)n + 1);
+	const size_t words = (size_t)gy + (size_t)n;
+	for (int r = 0; r < n; ++r) {
+		SphSim *s = hs[r];
+		DeviceScope dev(s);
+		const GridDesc &g = s->grid;
+		if (!s->dRowCounts) CU(s, cudaMalloc(&s->dRowCounts, words * sizeof(uint32_t)));
+		s->hRowCounts.resize(words);
+		CU(s, cudaMemsetAsync(s->dRowCounts, 0, words * sizeof(uint32_t), s->stream));
+		row_counts_kernel<<<(g.ownHi - g.ownLo + 255) / 256, 256, 0, s->stream>>>(g, s->cellStart, s->dRowCounts, r);
+		CU(s, cudaGetLastError());
+		CU(s, cudaMemcpyAsync(s->hRowCounts.data(), s->dRowCounts, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+		CU(s, cudaStreamSynchronize(s->stream));
+		for (int row = 0; row < gy; ++row) total[(size_t)row] += s->hRowCounts[(size_t)row];
+		oldB[(size_t)r] = g.ownLo;
+	}
+	oldB[(size_t)n] = gy;
+	const std::vector<int> nb = plan_strip_bounds(total.data(), gy, oldB, hs[0]->strip.halo, hs[0]->rebalanceMaxShift);
+	for (int r = 0; r < n; ++r) {
+		hs[r]->pendingRetarget = nb != oldB;
+		hs[r]->pendLo = nb[(size_t)r];
+		hs[r]->pendHi = nb[(size_t)r + 1];
+	}
+	return SPH_OK;
+}
+
 // Between the viscosity pass (previous grid, old rows) and the grid build of the same step: the rank's rows and its
 // window change; nothing is copied or reallocated (the cell arrays were sized for the whole grid).  predict_key_kernel
 // then keeps / sends by the new rows while authority still follows the old ones (StripDesc::authLo/authHi), and the one
@@ -678,7 +803,8 @@ void apply_retarget(SphSim *s) {
 	s->nTiles = (g.nCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE;
 	for (StepGraph &c : s->graphs) cudaGraphExecDestroy(c.exec); // the grid description is baked into every launch
 	s->graphs.clear();
-	s->haloMsgRecords = s->strip.haloCap; // this exchange also carries the rows that change hands: ship whole buffers once
+	s->gridGen++;
+	s->haloMsgRecords = s->strip.haloCap; // NCCL transport: this exchange also carries the rows that change hands, ship whole buffers once
 	s->pendingRetarget = false;
 	s->rebalances++;
 }
@@ -779,9 +905,18 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 512u;
 	s->sweepAdaptive = cfg->sweep_capacity == 0;
 	s->useGraphs = !(cfg->flags & SPH_FLAG_NO_GRAPHS);
-	if (s->sweepCap < 32 || s->sweepCap > 3072) {
-		delete s;
-		return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..3072", s->sweepCap);
+	{
+		// the viscosity sweep stages positions + velocities + a 16-bit queue: 18 bytes per candidate and warp
+		int smemOptin = 0, sms = 0;
+		cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+		if (sms > 0) s->numSMs = sms;
+		s->maxDynSmem = (size_t)std::min(std::max(smemOptin - 2048, 48 * 1024), 200 * 1024);
+		const uint32_t most = (uint32_t)(s->maxDynSmem / (SPH_SWEEP_WARPS * 18u)) / 32u * 32u;
+		if (s->sweepCap < 32 || s->sweepCap > most) {
+			delete s;
+			return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..%u (shared memory of device %d)", cfg->sweep_capacity, most, cfg->device);
+		}
 	}
 	GridDesc &g = s->grid;
 	g.halfW = cfg->domain_width * 0.5f;  // sph.h:21
@@ -790,8 +925,9 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	g.gx = (int)(cfg->domain_width / cfg->cell_size);  // sph.h:61
 	g.gy = (int)(cfg->domain_height / cfg->cell_size); // sph.h:62
 	if (g.gx < 1 || g.gy < 1 || g.gx > 65535 || g.gy > 65535) {
+		const int gx = g.gx, gy = g.gy;
 		delete s;
-		return fail(nullptr, SPH_ERR_INVALID, "grid %d x %d outside 1..65535", g.gx, g.gy);
+		return fail(nullptr, SPH_ERR_INVALID, "grid %d x %d outside 1..65535", gx, gy);
 	}
 	g.rowLo = g.ownLo = 0;
 	g.rowHi = g.ownHi = g.gy;
@@ -848,18 +984,18 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	}
 	if (cfg->world_size > 1) {
 		s->strip.haloCap = (uint32_t)(cfg->halo_capacity ? cfg->halo_capacity : std::max<uint64_t>(cap / 4, 4096));
-		s->haloBytes = sizeof(HaloBuffer) + (size_t)s->strip.haloCap * sizeof(HaloRecord);
-		for (int d = 0; d < 2; ++d) {
-			CUC(cudaMalloc(&s->sendBuf[d], s->haloBytes));
-			CUC(cudaMalloc(&s->recvBuf[d], s->haloBytes));
-			CUC(cudaMemset(s->sendBuf[d], 0, sizeof(HaloBuffer)));
-			CUC(cudaMemset(s->recvBuf[d], 0, sizeof(HaloBuffer)));
-		}
-		s->strip.sendDown = s->sendBuf[0];
-		s->strip.sendUp = s->sendBuf[1];
+		s->haloBytes = (sizeof(HaloBuffer) + (size_t)s->strip.haloCap * sizeof(HaloRecord) + 255u) & ~(size_t)255u;
+		CUC(cudaMalloc(&s->mail, 4 * s->haloBytes));
+		CUC(cudaMemset(s->mail, 0, 4 * s->haloBytes));
+		for (int side = 0; side < 2; ++side)
+			for (int par = 0; par < 2; ++par) s->mailIn[side][par] = reinterpret_cast<HaloBuffer *>(s->mail + (size_t)(side * 2 + par) * s->haloBytes);
 		s->haloMsgRecords = s->strip.haloCap;
-		CUC(cudaMalloc(&s->dPeak, 2 * sizeof(uint32_t)));
-		CUC(cudaMemset(s->dPeak, 0, 2 * sizeof(uint32_t)));
+		CUC(cudaMalloc(&s->dSendCount, 4 * sizeof(uint32_t)));
+		CUC(cudaMemset(s->dSendCount, 0, 4 * sizeof(uint32_t)));
+		s->strip.sendCount = s->dSendCount;
+		CUC(cudaMallocHost(&s->hPeak, sizeof(uint32_t)));
+		*s->hPeak = 0;
+		CUC(cudaEventCreateWithFlags(&s->peakEvent, cudaEventDisableTiming));
 		s->hostN = cap; // launch bound: the live count is only known on the device
 	}
 	CUC(cudaMalloc(&s->dOwnedCount, sizeof(uint32_t)));
@@ -875,6 +1011,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 
 int sph_destroy(SphHandle s) {
 	if (!s) return SPH_OK;
+	DeviceScope deviceScope__(s);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	if (s->copyStream) {
 		cudaStreamSynchronize(s->copyStream);
@@ -905,11 +1042,19 @@ int sph_destroy(SphHandle s) {
 	cudaFree(s->dRenderPos);
 	cudaFree(s->dRenderCol);
 	cudaFree(s->dCellXY);
-	for (int d = 0; d < 2; ++d) {
-		cudaFree(s->sendBuf[d]);
-		cudaFree(s->recvBuf[d]);
-	}
-	cudaFree(s->dPeak);
+	if (s->transport == TR_PEER)
+		for (int d = 0; d < 2; ++d)
+			if (s->peerBase[d]) cudaIpcCloseMemHandle(s->peerBase[d]);
+	for (SphSim *o : s->group) // strips of one process: the others must not publish into freed mailboxes
+		if (o != s) {
+			o->transport = TR_NONE;
+			o->group.clear();
+		}
+	cudaFree(s->mail);
+	cudaFree(s->sendMem);
+	cudaFree(s->dSendCount);
+	if (s->hPeak) cudaFreeHost(s->hPeak);
+	if (s->peakEvent) cudaEventDestroy(s->peakEvent);
 	cudaFree(s->dOwnedCount);
 	cudaFree(s->dOwnedIds);
 	if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
@@ -932,42 +1077,42 @@ int sph_destroy(SphHandle s) {
 
 // ---- parameters ---------------------------------------------------------------------------
 int sph_set_params(SphHandle s, const SphParams *p) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!p) return fail(s, SPH_ERR_INVALID, "null params");
 	s->params = *p;
 	s->params.inv_kernel_height = 1.0f / s->params.kernel_height; // copy-ctor, sph.h:100-110
 	return SPH_OK;
 }
 int sph_get_params(SphHandle s, SphParams *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	*out = s->params;
 	return SPH_OK;
 }
 int sph_set_gravity(SphHandle s, float gx, float gy) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->gravity = make_float2(gx, gy);
 	return SPH_OK;
 }
 int sph_add_external_force(SphHandle s, float fx, float fy) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->extForce.x += fx; // externalForce += force, demo4.h:189-191
 	s->extForce.y += fy;
 	return SPH_OK;
 }
 int sph_clear_external_force(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->extForce = make_float2(0, 0);
 	return SPH_OK;
 }
 int sph_set_relaxation(SphHandle s, float omega) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!(omega > 0.0f)) return fail(s, SPH_ERR_INVALID, "relaxation must be > 0");
 	s->omega = omega;
 	return SPH_OK;
 }
 int sph_grid_dims(SphHandle s, int32_t *gx, int32_t *gy) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (gx) *gx = s->grid.gx;
 	if (gy) *gy = s->grid.gy;
 	return SPH_OK;
@@ -975,34 +1120,34 @@ int sph_grid_dims(SphHandle s, int32_t *gx, int32_t *gy) {
 
 // ---- bodies ----------------------------------------------------------------------------------
 int sph_clear_bodies(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->bodies.clear();
 	s->bodiesDirty = true;
 	return SPH_OK;
 }
 int sph_add_plane(SphHandle s, float nx, float ny, float d) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	DevBody b = {};
 	b.type = BODY_PLANE;
 	b.f[0] = nx; b.f[1] = ny; b.f[2] = d;
 	return add_body(s, b);
 }
 int sph_add_circle(SphHandle s, float x, float y, float r) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	DevBody b = {};
 	b.type = BODY_CIRCLE;
 	b.f[0] = x; b.f[1] = y; b.f[2] = r;
 	return add_body(s, b);
 }
 int sph_add_segment(SphHandle s, float ax, float ay, float bx, float by) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	DevBody b = {};
 	b.type = BODY_SEGMENT;
 	b.f[0] = ax; b.f[1] = ay; b.f[2] = bx; b.f[3] = by;
 	return add_body(s, b);
 }
 int sph_add_polygon(SphHandle s, size_t n, const float *xy) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!xy || n < 3 || n > kMaxPolyVerts) return fail(s, SPH_ERR_INVALID, "polygon needs 3..%zu vertices (sph.h:161), got %zu", kMaxPolyVerts, n);
 	DevBody b = {};
 	b.type = BODY_POLYGON;
@@ -1011,14 +1156,14 @@ int sph_add_polygon(SphHandle s, size_t n, const float *xy) {
 	return add_body(s, b);
 }
 int sph_body_count(SphHandle s, size_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (out) *out = s->bodies.size();
 	return SPH_OK;
 }
 
 // ---- particles -------------------------------------------------------------------------------
 int sph_clear_particles(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->hostN = s->cfg.world_size > 1 ? s->capacity : 0;
 	s->nextId = 0;
 	s->accFrom = 0xFFFFFFFFu;
@@ -1030,13 +1175,13 @@ int sph_clear_particles(SphHandle s) {
 	return SPH_OK;
 }
 int sph_clear_emitters(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	s->emitters.clear();
 	return SPH_OK;
 }
 
 int sph_add_particles(SphHandle s, size_t n, const float *posXY, const float *accXY, uint64_t *firstIndex) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (n && !posXY) return fail(s, SPH_ERR_INVALID, "null positions");
 	if (s->cfg.world_size > 1) return fail(s, SPH_ERR_STATE, "host-side particle lists are single-GPU; use sph_add_volume_hashed with strips");
 	int rc = append_particles(s, n, posXY, accXY, firstIndex);
@@ -1054,7 +1199,7 @@ static inline void random_direction(float *x, float *y) { // Vec2RandomDirection
 }
 
 int sph_add_volume(SphHandle s, float cx, float cy, float fx, float fy, int countX, int countY, float spacing) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (countX <= 0 || countY <= 0) return SPH_OK; // zero-sized volumes add nothing (app.cpp:522 relies on it)
 	const float h = s->params.kernel_height; // the reference uses the constant kSPHKernelHeight (demo4.cpp:176); SetParams keeps them equal (sph.h:113)
 	std::vector<float> pos((size_t)countX * countY * 2), acc((size_t)countX * countY * 2);
@@ -1081,7 +1226,7 @@ int sph_add_volume(SphHandle s, float cx, float cy, float fx, float fy, int coun
 }
 
 int sph_add_volume_hashed(SphHandle s, float cx, float cy, float fx, float fy, int64_t countX, int64_t countY, float spacing, uint64_t seed) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (countX <= 0 || countY <= 0) return SPH_OK;
 	const uint64_t total = (uint64_t)countX * (uint64_t)countY;
 	if (s->nextId + total > 0xFFFFFF00ull) return fail(s, SPH_ERR_CAPACITY, "particle ids exceed 32 bits");
@@ -1119,7 +1264,7 @@ int sph_add_volume_hashed(SphHandle s, float cx, float cy, float fx, float fy, i
 }
 
 int sph_add_emitter(SphHandle s, float px, float py, float dx, float dy, float radius, float speed, float rate, float duration) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (s->emitters.size() >= kMaxEmitters) return fail(s, SPH_ERR_CAPACITY, "more than %zu emitters (demo4.cpp:156)", kMaxEmitters);
 	HostEmitter e = { px, py, dx, dy, radius, speed, rate, duration, 0.0f, 0.0f, 1 };
 	s->emitters.push_back(e);
@@ -1127,13 +1272,13 @@ int sph_add_emitter(SphHandle s, float px, float py, float dx, float dy, float r
 }
 
 int sph_local_particle_count(SphHandle s, uint64_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (s->cfg.world_size > 1) return sph_read_owned(s, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, out);
 	if (out) *out = s->hostN;
 	return SPH_OK;
 }
 int sph_particle_count(SphHandle s, uint64_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (out) *out = s->hostN;
 	return SPH_OK;
 }
@@ -1238,7 +1383,7 @@ extern "C" const char *sph_scenario_name(int idx) {
 	return scene_table()[(size_t)idx].name;
 }
 extern "C" int sph_load_scenario(SphHandle s, int idx, int seed) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (idx < 0 || idx >= (int)scene_table().size()) return fail(s, SPH_ERR_INVALID, "scenario %d of %zu", idx, scene_table().size());
 	const Scene &sc = scene_table()[(size_t)idx];
 	if (seed >= 0) srand((unsigned)seed);
@@ -1321,16 +1466,29 @@ static void set_buffer_parity(SphSim *s, uint32_t p) {
 }
 
 // ---- the hot path -------------------------------------------------------------------------------
-int sph_step(SphHandle s, float dt) {
-	CHECK_HANDLE(s);
+namespace {
+struct StepCtx {
+	float dt, invDt;
+	float2 force;
+	PairParams k;
+	unsigned nb;
+	bool graphable;
+};
+
+// host work ahead of a step's launches: emitters (demo4.cpp:296-299), body upload, staging capacity, strip bookkeeping
+int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
 	if (!(dt > 0.0f)) return fail(s, SPH_ERR_INVALID, "dt must be > 0");
-	if (s->cfg.world_size > 1 && !s->comm) return fail(s, SPH_ERR_STATE, "call sph_comm_init before stepping a multi-GPU handle");
+	if (s->cfg.world_size > 1 && s->transport == TR_NONE) return fail(s, SPH_ERR_STATE, "call sph_comm_init (or sph_comm_init_local) before stepping a multi-GPU handle");
 	if (s->cfg.world_size > 1 && !s->emitters.empty()) return fail(s, SPH_ERR_STATE, "emitters are single-GPU");
+	int rc;
 	if (!s->emitters.empty()) {
-		int rc = update_emitters(s, dt);
+		const auto t0 = std::chrono::steady_clock::now();
+		rc = update_emitters(s, dt);
 		if (rc != SPH_OK) return rc;
+		s->hostEmitterMs += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		s->hostEmitterSteps++;
 	}
-	int rc = upload_bodies(s);
+	rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
 	if (s->sweepAdaptive && s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
 		// shared-memory staging sized to twice the longest candidate list seen recently: a host that
@@ -1340,80 +1498,87 @@ int sph_step(SphHandle s, float dt) {
 		if (longest) s->sweepCap = std::min(1024u, std::max(192u, ((2u * longest + 31u) / 32u) * 32u));
 		s->lagPending = false;
 	}
-	const PairParams k = pair_params(s, dt);
-	const unsigned nb = blocks_for(s->hostN);
-	const float invDt = 1.0f / dt; // demo4.cpp:287
-	const float2 force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y); // gravity + externalForce, :306
-
-	// Steady state (nothing appended since the last step, no per-phase timing): the ~14
-	// launches of a step are replayed from a CUDA graph, which removes the launch gaps that dominate
-	// small scenes.  Kernel arguments depend on which half of each double buffer is current, so graphs
-	// are cached per buffer parity, staging capacity, dt, force and parameters.
+	c.dt = dt;
+	c.k = pair_params(s, dt);
+	c.nb = blocks_for(s->hostN);
+	c.invDt = 1.0f / dt; // demo4.cpp:287
+	c.force = make_float2(s->gravity.x + s->extForce.x, s->gravity.y + s->extForce.y); // gravity + externalForce, :306
 	if (s->cfg.world_size > 1) {
 		rc = maybe_resize_halo(s);
 		if (rc != SPH_OK) return rc;
 	}
-	if (s->cfg.world_size > 1 && s->rebalanceEvery > 0 && s->steppedOnce && s->steps % (uint64_t)s->rebalanceEvery == 0) {
+	if (planRebalance && s->cfg.world_size > 1 && s->rebalanceEvery > 0 && s->steppedOnce && s->steps % (uint64_t)s->rebalanceEvery == 0) {
 		rc = plan_rebalance(s);
 		if (rc != SPH_OK) return rc;
 	}
-	const bool graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2 && !s->pendingRetarget;
-	// One GPU: the whole step is one graph.  Strips: NCCL send/recv inside a captured stream dead-locked on
-	// this stack (NCCL 2.28.9, driver 580), so the launches before and after the exchange are two graphs
-	// and the exchange itself is enqueued plainly between them.
-	auto run_part = [&](int parts) -> int {
-		if (!graphable) return enqueue_step(s, dt, k, nb, force, invDt, parts);
-		StepGraphKey key;
-		memset(&key, 0, sizeof(key));
-		key.parity = buffer_parity(s);
-		key.sweepCap = s->sweepCap;
-		key.nb = nb;
-		key.nbodies = (uint32_t)s->bodies.size();
-		key.haloMsgRecords = s->haloMsgRecords;
-		key.parts = (uint32_t)parts;
-		key.flowEpoch = s->flowEpoch; // the sweep launches carry the pass number over the current grid as an argument
-		key.force = force;
-		key.k = k;
-		StepGraph *g = nullptr;
-		for (StepGraph &c : s->graphs)
-			if (memcmp(&c.key, &key, sizeof(key)) == 0) g = &c;
-		if (!g) {
-			if (s->graphs.size() >= 16) { // parameters keep changing: drop the oldest
-				cudaGraphExecDestroy(s->graphs.front().exec);
-				s->graphs.erase(s->graphs.begin());
-			}
-			cudaGraph_t graph = nullptr;
-			CU(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-			const int rce = enqueue_step(s, dt, k, nb, force, invDt, parts);
-			const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
-			if (rce != SPH_OK) return rce;
-			if (ce != cudaSuccess) return fail(s, SPH_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-			StepGraph made;
-			made.key = key;
-			made.parityAfter = buffer_parity(s);
-			made.flowEpochAfter = s->flowEpoch;
-			CU(s, cudaGraphInstantiate(&made.exec, graph, 0));
-			cudaGraphDestroy(graph);
-			set_buffer_parity(s, key.parity); // capture only recorded the launches: the state is still "before"
-			s->graphs.push_back(made);
-			g = &s->graphs.back();
+	// Steady state (nothing appended since the last step, no per-phase timing): the launches of a step are replayed
+	// from a CUDA graph, which removes the launch gaps that dominate small scenes.  Kernel arguments depend on which
+	// half of each double buffer is current, so graphs are cached per buffer parity, staging capacity, dt, force and
+	// parameters.  (The exchange's parity and sequence number live on the device: they are not part of the key.)
+	c.graphable = s->useGraphs && s->accFrom == 0xFFFFFFFFu && !(s->cfg.flags & SPH_FLAG_PHASE_TIMING) && s->steps >= 2 && !s->pendingRetarget;
+	return SPH_OK;
+}
+
+int step_run(SphSim *s, const StepCtx &c, int parts) {
+	if (!c.graphable) return enqueue_step(s, c.dt, c.k, c.nb, c.force, c.invDt, parts);
+	StepGraphKey key;
+	memset(&key, 0, sizeof(key));
+	key.parity = buffer_parity(s);
+	key.sweepCap = s->sweepCap;
+	key.nb = c.nb;
+	key.nbodies = (uint32_t)s->bodies.size();
+	key.haloMsgRecords = s->haloMsgRecords;
+	key.parts = (uint32_t)parts;
+	key.flowEpoch = s->flowEpoch; // the sweep launches carry the pass number over the current grid as an argument
+	key.gridGen = s->gridGen;
+	key.force = c.force;
+	key.k = c.k;
+	StepGraph *g = nullptr;
+	for (StepGraph &cand : s->graphs)
+		if (memcmp(&cand.key, &key, sizeof(key)) == 0) g = &cand;
+	if (!g) {
+		if (s->graphs.size() >= 16) { // parameters keep changing: drop the oldest
+			cudaGraphExecDestroy(s->graphs.front().exec);
+			s->graphs.erase(s->graphs.begin());
 		}
-		CU(s, cudaGraphLaunch(g->exec, s->stream));
-		set_buffer_parity(s, g->parityAfter);
-		s->flowEpoch = g->flowEpochAfter;
-		return SPH_OK;
-	};
-	if (s->cfg.world_size == 1) {
-		rc = run_part(GRID_ALL);
-		if (rc != SPH_OK) return rc;
-	} else {
-		rc = run_part(GRID_FRONT);
-		if (rc != SPH_OK) return rc;
-		rc = enqueue_step(s, dt, k, nb, force, invDt, GRID_EXCHANGE);
-		if (rc != SPH_OK) return rc;
-		rc = run_part(GRID_BACK);
-		if (rc != SPH_OK) return rc;
+		cudaGraph_t graph = nullptr;
+		const uint32_t epochBefore = s->flowEpoch;
+		const uint64_t exchangesBefore = s->exchanges;
+		const int32_t authLo = s->strip.authLo, authHi = s->strip.authHi;
+		CU(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+		const int rce = enqueue_step(s, c.dt, c.k, c.nb, c.force, c.invDt, parts);
+		const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+		StepGraph made;
+		made.key = key;
+		made.parityAfter = buffer_parity(s);
+		made.flowEpochAfter = s->flowEpoch;
+		made.exchanges = (uint32_t)(s->exchanges - exchangesBefore);
+		// capture only recorded the launches: the host-side state is still "before"
+		set_buffer_parity(s, key.parity);
+		s->flowEpoch = epochBefore;
+		s->exchanges = exchangesBefore;
+		cudaError_t ci = cudaSuccess;
+		if (rce == SPH_OK && ce == cudaSuccess) ci = cudaGraphInstantiate(&made.exec, graph, 0);
+		if (graph) cudaGraphDestroy(graph);
+		if (rce != SPH_OK || ce != cudaSuccess || ci != cudaSuccess) {
+			s->strip.authLo = authLo;
+			s->strip.authHi = authHi;
+			cudaGetLastError();
+			if (rce != SPH_OK) return rce;
+			return fail(s, SPH_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ci));
+		}
+		s->graphs.push_back(made);
+		g = &s->graphs.back();
 	}
+	CU(s, cudaGraphLaunch(g->exec, s->stream));
+	set_buffer_parity(s, g->parityAfter);
+	s->flowEpoch = g->flowEpochAfter;
+	s->exchanges += g->exchanges;
+	if (parts & GRID_FRONT) s->accFrom = 0xFFFFFFFFu;
+	return SPH_OK;
+}
+
+int step_finish(SphSim *s) {
 	CU(s, cudaGetLastError());
 	s->steps++;
 	s->steppedOnce = true;
@@ -1422,7 +1587,6 @@ int sph_step(SphHandle s, float dt) {
 		CU(s, cudaEventRecord(s->lagEvent, s->stream));
 		s->lagPending = true;
 	}
-
 	if (s->cfg.flags & SPH_FLAG_PHASE_TIMING) {
 		// event k+1 closes phase k; the exchange sits between predict and scan, so its event (index
 		// PH_EXCHANGE+1) is the one that opens the scan
@@ -1437,9 +1601,64 @@ int sph_step(SphHandle s, float dt) {
 	}
 	return SPH_OK;
 }
+} // namespace
+
+int sph_step(SphHandle s, float dt) {
+	ENTER(s);
+	if (s->transport == TR_LOCAL) return fail(s, SPH_ERR_STATE, "strips of one process are stepped together: use sph_step_group");
+	StepCtx c;
+	int rc = step_prepare(s, dt, c, true);
+	if (rc != SPH_OK) return rc;
+	if (s->cfg.world_size == 1 || s->transport == TR_PEER) {
+		// one GPU, or strips that store their halo records straight into the neighbours' memory: the whole step is one graph
+		rc = step_run(s, c, GRID_ALL);
+		if (rc != SPH_OK) return rc;
+	} else {
+		// NCCL transport: send/recv inside a captured stream dead-locked on this stack (NCCL 2.28.9, driver 580), so the
+		// launches before and after the exchange are two graphs and the exchange itself is enqueued plainly between them
+		rc = step_run(s, c, GRID_FRONT);
+		if (rc != SPH_OK) return rc;
+		rc = exchange_nccl(s);
+		if (rc != SPH_OK) return rc;
+		rc = step_run(s, c, GRID_BACK);
+		if (rc != SPH_OK) return rc;
+	}
+	return step_finish(s);
+}
+
+// Strips that live in one process (sph_comm_init_local): every strip's launches up to the publication of its halo
+// records are enqueued before any strip's wait for them, so a waiting kernel never depends on work the host has
+// not enqueued yet - also when all strips share one GPU.
+int sph_step_group(SphHandle *handles, int32_t n, float dt) {
+	if (!handles || n < 1) return fail(nullptr, SPH_ERR_INVALID, "sph_step_group needs handles");
+	for (int r = 0; r < n; ++r) {
+		CHECK_HANDLE(handles[r]);
+		if (handles[r]->transport != TR_LOCAL || (int)handles[r]->group.size() != n || handles[r]->group[(size_t)r] != handles[r])
+			return fail(handles[r], SPH_ERR_STATE, "sph_step_group takes exactly the handles of one sph_comm_init_local call, in rank order");
+	}
+	SphSim *first = handles[0];
+	if (first->rebalanceEvery > 0 && first->steppedOnce && first->steps % (uint64_t)first->rebalanceEvery == 0) {
+		int rc = plan_rebalance_group(handles, n);
+		if (rc != SPH_OK) return rc;
+	}
+	std::vector<StepCtx> ctx((size_t)n);
+	for (int r = 0; r < n; ++r) {
+		DeviceScope dev(handles[r]);
+		int rc = step_prepare(handles[r], dt, ctx[(size_t)r], false);
+		if (rc == SPH_OK) rc = step_run(handles[r], ctx[(size_t)r], GRID_FRONT);
+		if (rc != SPH_OK) return rc;
+	}
+	for (int r = 0; r < n; ++r) {
+		DeviceScope dev(handles[r]);
+		int rc = step_run(handles[r], ctx[(size_t)r], GRID_BACK);
+		if (rc == SPH_OK) rc = step_finish(handles[r]);
+		if (rc != SPH_OK) return rc;
+	}
+	return SPH_OK;
+}
 
 int sph_sync(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	CU(s, cudaStreamSynchronize(s->stream));
 	CU(s, cudaStreamSynchronize(s->copyStream));
 	s->copyPending = false;
@@ -1447,7 +1666,7 @@ int sph_sync(SphHandle s) {
 }
 
 int sph_run_pass(SphHandle s, int pass, float dt) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	int rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
 	const bool exact = s->cfg.fp_mode == SPH_FP_EXACT;
@@ -1466,6 +1685,7 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 			predict_only_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), dt);
 			break;
 		case SPH_PASS_GRID:
+			if (s->transport == TR_LOCAL) return fail(s, SPH_ERR_STATE, "strips of one process exchange inside sph_step_group only");
 			if (s->cfg.world_size > 1) {
 				rc = maybe_resize_halo(s);
 				if (rc != SPH_OK) return rc;
@@ -1497,17 +1717,19 @@ int sph_run_pass(SphHandle s, int pass, float dt) {
 
 // ---- statistics ----------------------------------------------------------------------------------
 int sph_reset_stats(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	reset_stats_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
 	memset(s->phaseMs, 0, sizeof(s->phaseMs));
 	s->phaseSteps = 0;
+	s->hostEmitterMs = 0.0f;
+	s->hostEmitterSteps = 0;
 	s->steppedOnce = false;
 	CU(s, cudaGetLastError());
 	return SPH_OK;
 }
 
 int sph_get_stats(SphHandle s, SphStats *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	CU(s, cudaMemcpyAsync(s->hCtr, s->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, s->stream));
 	CU(s, cudaStreamSynchronize(s->stream));
@@ -1520,6 +1742,7 @@ int sph_get_stats(SphHandle s, SphStats *out) {
 	out->max_cell_particle_count = c.maxCell;
 	out->pair_candidates = c.pairCandidates;
 	out->steps = s->steps;
+	if (s->hostEmitterSteps) out->time_emitters = s->hostEmitterMs / (float)s->hostEmitterSteps; // host time of UpdateEmitter, ms per step (sph.h:132)
 	if (s->phaseSteps) {
 		const double inv = 1.0 / (double)s->phaseSteps;
 		out->time_integration = (float)(s->phaseMs[PH_INTEGRATE] * inv);
@@ -1533,6 +1756,7 @@ int sph_get_stats(SphHandle s, SphStats *out) {
 	}
 	if (c.lost)
 		return fail(s, SPH_ERR_STATE, "%u particle-steps left the rows this rank and its two neighbours hold (moved more than the halo in one step)", c.lost);
+	if (c.overflow & 8u) return fail(s, SPH_ERR_COMM, "a neighbour strip did not publish its halo records within %llu s", kHaloWaitTimeoutNs / 1000000000ull);
 	if (c.overflow)
 		return fail(s, SPH_ERR_CAPACITY, "device reported a capacity overflow (flags %u: 1 = particles, 2 = halo buffer, 4 = more candidates in one 3x3 block than the sweep queue holds)",
 		            c.overflow);
@@ -1540,7 +1764,7 @@ int sph_get_stats(SphHandle s, SphStats *out) {
 }
 
 int sph_get_phase_ms(SphHandle s, float out[SPH_NUM_PHASES], uint64_t *steps) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	for (int p = 0; p < PH_COUNT; ++p) out[p] = s->phaseSteps ? (float)(s->phaseMs[p] / (double)s->phaseSteps) : 0.0f;
 	if (steps) *steps = s->phaseSteps;
 	return SPH_OK;
@@ -1548,7 +1772,7 @@ int sph_get_phase_ms(SphHandle s, float out[SPH_NUM_PHASES], uint64_t *steps) {
 
 // ---- readback / injection -------------------------------------------------------------------------
 int sph_read_particles(SphHandle s, void *dst, size_t stride) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!dst || stride < sizeof(ParticleRecord)) return fail(s, SPH_ERR_INVALID, "stride must be >= 48");
 	if (s->nextId == 0) return SPH_OK;
 	if (!s->dRecords) CU(s, cudaMalloc(&s->dRecords, (size_t)s->capacity * sizeof(ParticleRecord)));
@@ -1562,7 +1786,7 @@ int sph_read_particles(SphHandle s, void *dst, size_t stride) {
 }
 
 int sph_write_particles(SphHandle s, const void *src, size_t stride) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!src || stride < sizeof(ParticleRecord)) return fail(s, SPH_ERR_INVALID, "stride must be >= 48");
 	if (s->cfg.world_size > 1) return fail(s, SPH_ERR_STATE, "state injection is single-GPU");
 	if (s->hostN == 0) return SPH_OK;
@@ -1582,7 +1806,7 @@ int sph_write_particles(SphHandle s, const void *src, size_t stride) {
 }
 
 int sph_render_particles(SphHandle s, void *positions, size_t posStride, void *colors, size_t colorStride) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if ((positions && posStride < sizeof(float2)) || (colors && colorStride < sizeof(float4))) return fail(s, SPH_ERR_INVALID, "stride too small");
 	if (s->nextId == 0) return SPH_OK;
 	if (!s->dRenderPos) {
@@ -1606,13 +1830,13 @@ int sph_render_particles(SphHandle s, void *positions, size_t posStride, void *c
 }
 
 int sph_wait_render(SphHandle s) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (s->copyPending) CU(s, cudaEventSynchronize(s->copyDone));
 	return SPH_OK;
 }
 
 int sph_read_cell_start(SphHandle s, uint32_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	CU(s, cudaMemcpyAsync(out, s->cellStart, ((size_t)s->grid.nCells + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
 	CU(s, cudaStreamSynchronize(s->stream));
@@ -1620,7 +1844,7 @@ int sph_read_cell_start(SphHandle s, uint32_t *out) {
 }
 
 int sph_read_cell_counts(SphHandle s, uint32_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	std::vector<uint32_t> start((size_t)s->grid.nCells + 1);
 	int rc = sph_read_cell_start(s, start.data());
@@ -1630,7 +1854,7 @@ int sph_read_cell_counts(SphHandle s, uint32_t *out) {
 }
 
 int sph_read_sorted_ids(SphHandle s, uint32_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	if (s->hostN == 0) return SPH_OK;
 	CU(s, cudaMemcpyAsync(out, s->id.in(), (size_t)s->hostN * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -1639,7 +1863,7 @@ int sph_read_sorted_ids(SphHandle s, uint32_t *out) {
 }
 
 int sph_read_cell_of_particle(SphHandle s, int32_t *out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!out) return fail(s, SPH_ERR_INVALID, "null out");
 	if (s->nextId == 0) return SPH_OK;
 	if (!s->dCellXY) CU(s, cudaMalloc(&s->dCellXY, (size_t)s->capacity * sizeof(int2)));
@@ -1660,18 +1884,18 @@ int sph_host_alloc(void **out, size_t bytes) {
 int sph_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? SPH_OK : SPH_ERR_CUDA; }
 
 int sph_get_stream(SphHandle s, void **out) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (out) *out = (void *)s->stream;
 	return SPH_OK;
 }
 int sph_mark(SphHandle s, int slot) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (slot < 0 || slot >= 8) return fail(s, SPH_ERR_INVALID, "mark slot 0..7");
 	CU(s, cudaEventRecord(s->marks[slot], s->stream));
 	return SPH_OK;
 }
 int sph_elapsed_ms(SphHandle s, int a, int b, float *ms) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms) return fail(s, SPH_ERR_INVALID, "mark slot 0..7");
 	CU(s, cudaEventSynchronize(s->marks[b]));
 	CU(s, cudaEventElapsedTime(ms, s->marks[a], s->marks[b]));
@@ -1688,24 +1912,140 @@ int sph_comm_unique_id(uint8_t id128[128]) {
 	memcpy(id128, id.internal, 128);
 	return SPH_OK;
 }
+// out-boxes of rank r: the lower neighbour's "from above" boxes and the upper neighbour's "from below" boxes
+static void wire_outboxes(SphSim *s, unsigned char *lowerMail, unsigned char *upperMail) {
+	for (int par = 0; par < 2; ++par) {
+		s->strip.outDown[par] = lowerMail ? reinterpret_cast<HaloBuffer *>(lowerMail + (size_t)(1 * 2 + par) * s->haloBytes) : nullptr;
+		s->strip.outUp[par] = upperMail ? reinterpret_cast<HaloBuffer *>(upperMail + (size_t)(0 * 2 + par) * s->haloBytes) : nullptr;
+	}
+}
+
 int sph_comm_init(SphHandle s, const uint8_t id128[128]) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!id128) return fail(s, SPH_ERR_INVALID, "null id");
 	if (s->cfg.world_size < 2) return fail(s, SPH_ERR_STATE, "sph_comm_init needs world_size > 1");
-	if (s->comm) return fail(s, SPH_ERR_STATE, "communicator already initialised");
+	if (s->comm || s->transport != TR_NONE) return fail(s, SPH_ERR_STATE, "communicator already initialised");
 	if (!g_nccl.load()) return fail(s, SPH_ERR_COMM, "%s", g_nccl.error.c_str());
+	NcclApi &nc = g_nccl;
 	NcclUniqueId id;
 	memcpy(id.internal, id128, 128);
 	CU(s, cudaSetDevice(s->cfg.device));
-	const int rc = g_nccl.CommInitRank(&s->comm, s->cfg.world_size, id, s->cfg.rank);
+	const int world = s->cfg.world_size, rank = s->cfg.rank;
+	int rc = nc.CommInitRank(&s->comm, world, id, rank);
 	if (rc != 0) {
 		s->comm = nullptr;
-		return fail(s, SPH_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+		return fail(s, SPH_ERR_COMM, "ncclCommInitRank: %s", nc.GetErrorString(rc));
+	}
+	// Everything that would otherwise connect lazily inside the first steps happens here: an all-gather (it also
+	// carries the IPC handles of the mailboxes), an all-reduce, and one send/recv with each neighbour.
+	struct Hello {
+		cudaIpcMemHandle_t mem;
+		uint64_t haloBytes;
+		int32_t ipcOk, pad;
+	};
+	Hello mine = {};
+	mine.haloBytes = s->haloBytes;
+	const bool wantPeer = !(s->cfg.flags & SPH_FLAG_EXCHANGE_NCCL);
+	mine.ipcOk = (wantPeer && cudaIpcGetMemHandle(&mine.mem, s->mail) == cudaSuccess) ? 1 : 0;
+	cudaGetLastError();
+	Hello *dHello = nullptr;
+	std::vector<Hello> all((size_t)world);
+	CU(s, cudaMalloc(&dHello, (size_t)(world + 1) * sizeof(Hello)));
+	CU(s, cudaMemcpyAsync(dHello + world, &mine, sizeof(Hello), cudaMemcpyHostToDevice, s->stream));
+	rc = nc.AllGather(dHello + world, dHello, sizeof(Hello), kNcclUint8, s->comm, s->stream);
+	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL all-gather failed: %s", nc.GetErrorString(rc));
+	CU(s, cudaMemcpyAsync(all.data(), dHello, (size_t)world * sizeof(Hello), cudaMemcpyDeviceToHost, s->stream));
+	CU(s, cudaStreamSynchronize(s->stream));
+	for (int r = 0; r < world; ++r)
+		if (all[(size_t)r].haloBytes != s->haloBytes) {
+			cudaFree(dHello);
+			return fail(s, SPH_ERR_INVALID, "rank %d was created with a different halo_capacity (%llu vs %llu bytes per mailbox)", r,
+			            (unsigned long long)all[(size_t)r].haloBytes, (unsigned long long)s->haloBytes);
+		}
+	// map the neighbours' mailboxes
+	uint32_t ok = wantPeer ? 1u : 0u;
+	for (int d = 0; d < 2 && ok; ++d) {
+		const int nbr = d == 0 ? rank - 1 : rank + 1;
+		if (nbr < 0 || nbr >= world) continue;
+		if (!all[(size_t)nbr].ipcOk || cudaIpcOpenMemHandle(&s->peerBase[d], all[(size_t)nbr].mem, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			s->peerBase[d] = nullptr;
+			ok = 0u;
+		}
+	}
+	cudaGetLastError();
+	// all ranks must agree on the transport: one refusal (no peer access between two GPUs, IPC not permitted) sends everybody to NCCL
+	uint32_t *dOk = reinterpret_cast<uint32_t *>(dHello);
+	CU(s, cudaMemcpyAsync(dOk, &ok, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+	rc = nc.AllReduce(dOk, dOk, 1, kNcclUint32, kNcclMin, s->comm, s->stream);
+	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL all-reduce failed: %s", nc.GetErrorString(rc));
+	CU(s, cudaMemcpyAsync(&ok, dOk, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+	// neighbour connections (used by the NCCL transport every step, by the peer transport never again)
+	rc = nc.GroupStart();
+	for (int d = 0; d < 2 && rc == 0; ++d) {
+		const int nbr = d == 0 ? rank - 1 : rank + 1;
+		if (nbr < 0 || nbr >= world) continue;
+		rc = nc.Send(dHello + world, sizeof(Hello), kNcclUint8, nbr, s->comm, s->stream);
+		if (rc == 0) rc = nc.Recv(dHello + (size_t)nbr, sizeof(Hello), kNcclUint8, nbr, s->comm, s->stream);
+	}
+	const int rcEnd = nc.GroupEnd();
+	if (rc == 0) rc = rcEnd;
+	if (rc != 0) return fail(s, SPH_ERR_COMM, "NCCL neighbour hand-shake failed: %s", nc.GetErrorString(rc));
+	CU(s, cudaStreamSynchronize(s->stream));
+	cudaFree(dHello);
+	if (ok) {
+		s->transport = TR_PEER;
+		wire_outboxes(s, static_cast<unsigned char *>(s->peerBase[0]), static_cast<unsigned char *>(s->peerBase[1]));
+	} else {
+		for (int d = 0; d < 2; ++d)
+			if (s->peerBase[d]) {
+				cudaIpcCloseMemHandle(s->peerBase[d]);
+				s->peerBase[d] = nullptr;
+			}
+		CU(s, cudaMalloc(&s->sendMem, 4 * s->haloBytes));
+		CU(s, cudaMemset(s->sendMem, 0, 4 * s->haloBytes));
+		s->transport = TR_NCCL;
+		// local send buffers laid out like a mailbox block, so the same wiring applies
+		wire_outboxes(s, rank > 0 ? s->sendMem : nullptr, rank + 1 < world ? s->sendMem : nullptr);
+	}
+	return SPH_OK;
+}
+
+// All strips of a simulation inside ONE process (one host thread driving several GPUs, or several strips on one GPU
+// for tests): the mailboxes are wired with plain pointers (peer access enabled between distinct devices) and the
+// strips are stepped together with sph_step_group.
+int sph_comm_init_local(SphHandle *handles, int32_t n) {
+	if (!handles || n < 2) return fail(nullptr, SPH_ERR_INVALID, "sph_comm_init_local needs >= 2 handles");
+	for (int r = 0; r < n; ++r) {
+		SphSim *s = handles[r];
+		ENTER(s);
+		if (s->cfg.world_size != n || s->cfg.rank != r) return fail(s, SPH_ERR_INVALID, "handle %d of the group has rank %d of %d", r, s->cfg.rank, s->cfg.world_size);
+		if (s->transport != TR_NONE) return fail(s, SPH_ERR_STATE, "communicator already initialised");
+		if (s->haloBytes != handles[0]->haloBytes) return fail(s, SPH_ERR_INVALID, "the strips were created with different halo capacities");
+	}
+	for (int r = 0; r + 1 < n; ++r) {
+		const int a = handles[r]->cfg.device, b = handles[r + 1]->cfg.device;
+		if (a == b) continue;
+		for (int dir = 0; dir < 2; ++dir) {
+			const int from = dir ? b : a, to = dir ? a : b;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, from, to);
+			if (!can) return fail(handles[r], SPH_ERR_COMM, "device %d cannot access device %d's memory", from, to);
+			cudaSetDevice(from);
+			const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(handles[r], SPH_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", from, to, cudaGetErrorString(e));
+			cudaGetLastError();
+		}
+	}
+	for (int r = 0; r < n; ++r) {
+		SphSim *s = handles[r];
+		s->transport = TR_LOCAL;
+		s->group.assign(handles, handles + n);
+		wire_outboxes(s, r > 0 ? handles[r - 1]->mail : nullptr, r + 1 < n ? handles[r + 1]->mail : nullptr);
 	}
 	return SPH_OK;
 }
 int sph_set_strip(SphHandle s, int32_t rowBegin, int32_t rowEnd) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (s->nextId != 0) return fail(s, SPH_ERR_STATE, "set the strip before adding particles");
 	CU(s, cudaStreamSynchronize(s->stream));
 	return configure_strip(s, rowBegin, rowEnd);
@@ -1714,7 +2054,7 @@ int sph_set_strip(SphHandle s, int32_t rowBegin, int32_t rowEnd) {
 // the particles this rank owns, compacted (arbitrary order) with their creation ids; any output may be NULL
 int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, void *positions, size_t posStride, void *colors, size_t colStride,
                    uint64_t *count) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if ((records && recStride < sizeof(ParticleRecord)) || (positions && posStride < sizeof(float2)) || (colors && colStride < sizeof(float4)))
 		return fail(s, SPH_ERR_INVALID, "stride too small");
 	const size_t cap = s->capacity;
@@ -1747,7 +2087,7 @@ int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, 
 // owned particles only exists on the device; the copies ship 1.1 x the previous frame's count (+4096) and
 // sph_wait_render_owned fetches the rest in the rare frame that outgrew it.  The first frame is read synchronously.
 int sph_render_owned(SphHandle s, uint32_t *ids, void *positions, size_t posStride, void *colors, size_t colStride) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!ids || !positions || !colors) return fail(s, SPH_ERR_INVALID, "sph_render_owned needs ids, positions and colours");
 	if (posStride < sizeof(float2) || colStride < sizeof(float4)) return fail(s, SPH_ERR_INVALID, "stride too small");
 	if (s->ownedPending) return fail(s, SPH_ERR_STATE, "sph_wait_render_owned was not called for the previous frame");
@@ -1795,7 +2135,7 @@ int sph_render_owned(SphHandle s, uint32_t *ids, void *positions, size_t posStri
 }
 
 int sph_wait_render_owned(SphHandle s, uint64_t *count) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (!s->ownedPending) return fail(s, SPH_ERR_STATE, "no sph_render_owned frame in flight");
 	if (s->copyPending) CU(s, cudaEventSynchronize(s->copyDone));
 	const uint64_t n = std::min<uint64_t>(*s->hOwnedCount, s->capacity);
@@ -1824,7 +2164,7 @@ int sph_plan_strip_bounds(const uint32_t *rowCounts, int32_t gridY, const int32_
 }
 
 int sph_set_rebalance(SphHandle s, int32_t everySteps, int32_t maxShiftRows) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (everySteps < 0 || maxShiftRows < 0) return fail(s, SPH_ERR_INVALID, "negative argument");
 	if (s->cfg.world_size == 1 || everySteps == 0) {
 		s->rebalanceEvery = 0;
@@ -1842,7 +2182,7 @@ int sph_set_rebalance(SphHandle s, int32_t everySteps, int32_t maxShiftRows) {
 }
 
 int sph_get_strip(SphHandle s, int32_t *rowBegin, int32_t *rowEnd) {
-	CHECK_HANDLE(s);
+	ENTER(s);
 	if (rowBegin) *rowBegin = s->grid.ownLo;
 	if (rowEnd) *rowEnd = s->grid.ownHi;
 	return SPH_OK;

@@ -58,7 +58,7 @@ def block_scene(nx, ny=None, spacing=0.1, gravity=(0.0, -10.0), seed=1337, fp_mo
 
 def block_strips(sim, world_size):
     """Row ranges [(lo, hi)] that split the block's rows evenly (the last strip also owns the empty
-    rows above the block).  Static: SURVEY.md 8(e)'s periodic rebalancing is future work."""
+    rows above the block).  The starting split; sph_set_rebalance moves it with the fluid."""
     sc = sim.scene
     gx, gy = sim.grid_dims()
     rows = min(gy, int(np.ceil((sc["ny"] * sc["spacing"] + 0.1) / KERNEL_HEIGHT)) + 1)

@@ -367,4 +367,65 @@ def pinned_empty(shape, dtype=np.float32):
                 lib.sph_host_free(self.p)
                 self.p = None
 
+        def __del__(self):  # page-locked memory must not outlive its last reference
+            try:
+                self.free()
+            except Exception:
+                pass
+
     return arr, _Owner(ptr)
+
+
+class StripGroup:
+    """All y-strips of one simulation inside ONE process (sph_comm_init_local / sph_step_group): one host thread
+    drives several GPUs the way the reference's single-threaded app loop would (app.cpp:228-236), or - for tests -
+    several strips share one GPU.  `sims` are ParticleSimulation objects created with rank = 0..n-1, world_size = n."""
+
+    def __init__(self, sims):
+        self.sims = list(sims)
+        self._lib = _lib.load()
+        self._arr = (_lib.c_vp * len(self.sims))(*[s._h for s in self.sims])
+        rc = self._lib.sph_comm_init_local(self._arr, len(self.sims))
+        if rc != _lib.SPH_OK:
+            self._raise(rc)
+
+    def _raise(self, rc):
+        buf = C.create_string_buffer(512)
+        for s in self.sims:  # the failing handle carries the text
+            self._lib.sph_last_error(s._h, buf, 512)
+            if buf.value:
+                break
+        else:
+            self._lib.sph_last_error(None, buf, 512)
+        raise SphError(rc, buf.value.decode(errors="replace"))
+
+    def Update(self, deltaTime):
+        rc = self._lib.sph_step_group(self._arr, len(self.sims), deltaTime)
+        if rc != _lib.SPH_OK:
+            self._raise(rc)
+
+    def Sync(self):
+        for s in self.sims:
+            s.Sync()
+
+    def close(self):
+        for s in self.sims:
+            s.close()
+
+
+def bind_host_to_gpu(device):
+    """Pins the calling process to the CPU cores next to GPU `device` (NVML's ideal affinity), so that page-locked
+    readback buffers allocated afterwards land on that GPU's NUMA node.  Host-side placement only; returns True
+    if the affinity was applied."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = int(vis.split(",")[device]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        return True
+    except Exception:
+        return False

@@ -105,4 +105,8 @@ def plan_bounds(row_counts, old_bounds, halo, max_shift=2):
         nb[b] = min(nb[b], nb[b + 1] - min_rows)
     if any(nb[b] - nb[b - 1] < min_rows for b in range(1, world + 1)):
         return old
+    # the fix-up passes may have pushed a boundary past the shift / halo limits (strips that start thinner than
+    # min_rows): never trade a correct split for a better balanced one
+    if any(abs(nb[b] - old[b]) > max_shift or nb[b] < old[b - 1] + halo or nb[b] > old[b + 1] - halo for b in range(1, world)):
+        return old
     return nb

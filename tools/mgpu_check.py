@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from nbodysimulation_experiment_b200 import SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER, ParticleSimulation, scenes  # noqa: E402
+from nbodysimulation_experiment_b200 import SPH_SOLVER_COLORED_GS, SPH_SOLVER_GATHER, ParticleSimulation, _lib, scenes  # noqa: E402
 
 
 def main():
@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--halo-rows", type=int, default=0)
     ap.add_argument("--rebalance", type=int, default=0, help="re-balance the strips every N steps (0 = static strips)")
     ap.add_argument("--max-shift", type=int, default=2)
+    ap.add_argument("--ny", type=int, default=0, help="block height in particles (default: nx); tall blocks give many strips enough rows")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="strip exchange: peer-memory mailboxes (default) or NCCL messages")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -39,8 +41,11 @@ def main():
     # every strip is given room for the whole scene twice over (what it holds + what arrives behind it in one step) and
     # for whole-scene exchange messages: under g = -10 the column falls into the bottom strips, and the default sizing
     # (3x the even share) overflows from 4 strips on
-    sim = scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, a.gravity), device=local, rank=rank, world_size=world, solver=solver,
-                             halo_rows=a.halo_rows, capacity=2 * a.nx * a.nx + 1024, halo_capacity=a.nx * a.nx)
+    ny = a.ny or a.nx
+    n_total = a.nx * ny
+    flags = _lib.SPH_FLAG_EXCHANGE_NCCL if a.transport == "nccl" else 0
+    sim = scenes.block_scene(a.nx, ny=ny, spacing=a.spacing, gravity=(0.0, a.gravity), device=local, rank=rank, world_size=world, solver=solver,
+                             halo_rows=a.halo_rows, capacity=2 * n_total + 1024, halo_capacity=n_total, flags=flags)
     uid = [ParticleSimulation.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim.comm_init(uid[0])
@@ -49,7 +54,6 @@ def main():
     if a.rebalance:
         sim.set_rebalance(a.rebalance, a.max_shift)
     scenes.fill_block(sim)
-    n_total = a.nx * a.nx
     counts = [None] * world
     dist.all_gather_object(counts, sim.local_particle_count())
     if rank == 0:
@@ -84,12 +88,13 @@ def main():
         assert len(ids) == n_total and len(np.unique(ids)) == n_total, "ownership is not a partition of the particles"
         multi = np.zeros((n_total, 12), np.float32)
         multi[ids] = rec
-        one = scenes.fill_block(scenes.block_scene(a.nx, spacing=a.spacing, gravity=(0.0, a.gravity), device=local, solver=solver))
+        one = scenes.fill_block(scenes.block_scene(a.nx, ny=ny, spacing=a.spacing, gravity=(0.0, a.gravity), device=local, solver=solver))
         for _ in range(a.steps):
             one.Update(dt)
         ref = one.particles()
         same = (multi.view(np.uint32) == ref.view(np.uint32)) | ((multi == 0) & (ref == 0))
         bad = np.argwhere(~same.all(1)).ravel()
+        print(f"exchange transport: {a.transport}", flush=True)
         print(f"{world}-GPU vs 1-GPU after {a.steps} steps: {len(bad)} of {n_total} particles differ; max abs diff {np.abs(multi - ref).max():.3e}", flush=True)
         if len(bad):
             rows = ((ref[bad, 1] + one.scene['height'] / 2) / scenes.KERNEL_HEIGHT).astype(int)
