@@ -224,8 +224,15 @@ def run_ours(args):
 
         # ---- e2e: Update + Render readback (positions + colours) into host memory every step, the per-frame
         # traffic of the reference's app loop (app.cpp:231-233,286-289).  One GPU: creation-order arrays in pinned
-        # memory.  Strips: each rank reads back the particles it owns (compacted, with their ids). ----------------
-        e2e_steps = max(3, min(steps, 32))
+        # memory.  Strips: each rank reads back the particles it owns (compacted, with their ids).
+        # The SAME steps of the scene as the device-timed leg (a fresh simulation, the same warm-up): the step cost
+        # of a collapsing column grows with the step number, and the two numbers are meant to differ by the readback
+        # alone. ------------------------------------------------------------------------------------------------
+        sim.close()
+        sim = make()
+        for _ in range(warmup):
+            sim.Update(DT)
+        e2e_steps = steps
         params_blob = np.zeros(16, np.float32)  # per-step host inputs: dt, gravity, external force
         d2h = 0
         if world == 1:

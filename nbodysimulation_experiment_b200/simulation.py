@@ -54,6 +54,7 @@ class ParticleSimulation:
         self._h = _lib.c_vp()
         self._check(self._lib.sph_create(C.byref(cfg), C.byref(self._h)), None)
         self._multithreading = True
+        self.bodies = []
 
     # -- plumbing ------------------------------------------------------------------------
     def _check(self, rc, handle="self"):
@@ -86,6 +87,7 @@ class ParticleSimulation:
 
     def ClearBodies(self):
         self._check(self._lib.sph_clear_bodies(self._h))
+        self.bodies = []
 
     def ClearParticles(self):
         self._check(self._lib.sph_clear_particles(self._h))
@@ -93,18 +95,24 @@ class ParticleSimulation:
     def ClearEmitters(self):
         self._check(self._lib.sph_clear_emitters(self._h))
 
+    # (`self.bodies` mirrors what was added through this object, in insertion order, as float32 values: tests hand the
+    # same bodies to the CPU oracle; LoadScenario adds its bodies inside the library and does not record them)
     def AddPlane(self, normal, distance):
         self._check(self._lib.sph_add_plane(self._h, normal[0], normal[1], distance))
+        self.bodies.append(("plane", float(np.float32(normal[0])), float(np.float32(normal[1])), float(np.float32(distance))))
 
     def AddCircle(self, pos, radius):
         self._check(self._lib.sph_add_circle(self._h, pos[0], pos[1], radius))
+        self.bodies.append(("circle", float(np.float32(pos[0])), float(np.float32(pos[1])), float(np.float32(radius))))
 
     def AddLineSegment(self, a, b):
         self._check(self._lib.sph_add_segment(self._h, a[0], a[1], b[0], b[1]))
+        self.bodies.append(("segment", float(np.float32(a[0])), float(np.float32(a[1])), float(np.float32(b[0])), float(np.float32(b[1]))))
 
     def AddPolygon(self, verts):
         v = np.ascontiguousarray(verts, np.float32).reshape(-1)
         self._check(self._lib.sph_add_polygon(self._h, len(v) // 2, v.ctypes.data))
+        self.bodies.append(("polygon", v.copy()))
 
     def AddParticle(self, position, force=(0.0, 0.0)):
         return self.AddParticles(np.array([position], np.float32), np.array([force], np.float32))

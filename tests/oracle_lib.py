@@ -101,6 +101,7 @@ class CpuSim:
             self._bind("step", None, [vp, f32])
             self._bind("step_timed", C.c_double, [vp, f32, C.c_int])
             self._bind("grid_dims", None, [vp, vp])
+            self._bind("add_particles", C.c_uint64, [vp, C.c_uint64, vp, vp])
             for p in ("update_grid", "neighbor_search", "density", "collide"):
                 self._bind("pass_" + p, None, [vp])
             for p in ("viscosity", "delta"):
@@ -239,6 +240,24 @@ class CpuSim:
             self.get_body(i, C.addressof(t), C.addressof(nv), f.ctypes.data)
             res.append((t.value, nv.value, f))
         return res
+
+    def add_particle_array(self, pos_xy, acc_xy=None):
+        """bulk AddParticle (oracle only): creation order = row order"""
+        pos = np.ascontiguousarray(pos_xy, np.float32).reshape(-1, 2)
+        acc = None if acc_xy is None else np.ascontiguousarray(acc_xy, np.float32).reshape(-1, 2)
+        return self.add_particles(len(pos), pos.ctypes.data, None if acc is None else acc.ctypes.data)
+
+    def add_bodies(self, bodies):
+        """bodies as recorded by nbodysimulation_experiment_b200.ParticleSimulation.bodies, in insertion order"""
+        for b in bodies:
+            if b[0] == "plane":
+                self.add_plane(b[1], b[2], b[3])
+            elif b[0] == "circle":
+                self.add_circle(b[1], b[2], b[3])
+            elif b[0] == "segment":
+                self.add_segment(b[1], b[2], b[3], b[4])
+            else:
+                self.polygon(b[1])
 
     def polygon(self, xy):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1)

@@ -308,12 +308,20 @@ def test_million_particle_invariants(pkg):
     assert np.isfinite(p).all()
     w, h = gpu.scene["width"], gpu.scene["height"]
     assert (np.abs(p[:, 0]) <= w / 2).all() and (np.abs(p[:, 1]) <= h / 2).all()  # planes keep everything inside
-    # cell of each particle recomputed on the host with the reference formula (sph.h:450-463)
-    hw, hh, cell = np.float32(w) * np.float32(0.5), np.float32(h) * np.float32(0.5), np.float32(scenes.KERNEL_HEIGHT)
     st = gpu.GetStats()
     assert st.max_particle_neighbor_count >= st.min_particle_neighbor_count > 0
+    assert 0 < st.min_cell_particle_count <= st.max_cell_particle_count  # running min/max of demo4.cpp:64-67
+    # cell of each particle recomputed on the host with the reference formula (sph.h:450-463): the grid is re-filed
+    # from the final positions (the step's own grid was filed from the predicted ones, demo4.cpp:342-356)
+    gpu.RunPass(pkg._lib.PASS_GRID, DT)
+    hw, hh, cell = np.float32(w) * np.float32(0.5), np.float32(h) * np.float32(0.5), np.float32(scenes.KERNEL_HEIGHT)
+    hx = np.clip(((p[:, 0] + hw) / cell).astype(np.int32), 0, gx - 1)  # float32 arithmetic, truncation toward zero, clamp
+    hy = np.clip(((p[:, 1] + hh) / cell).astype(np.int32), 0, gy - 1)
+    cells = gpu.cell_of_particle()
+    assert np.array_equal(cells[:, 0], hx) and np.array_equal(cells[:, 1], hy)
+    counts = np.bincount(hy.astype(np.int64) * gx + hx, minlength=gx * gy)
+    assert np.array_equal(gpu.cell_counts(), counts.astype(np.uint32))
     gpu.close()
-    del hw, hh, cell
 
 
 # ---- the coloured Gauss-Seidel sweeps -------------------------------------------------------------
@@ -362,20 +370,19 @@ def test_colored_block_bitwise_vs_oracle(pkg, sweep):
 
 
 def test_colored_solver_tracks_reference_energy(pkg):
-    """Statistical parity with the REFERENCE's own single-thread run of its default scene (golden
-    dump): the coloured sweep is a different, equally legitimate in-place order, so trajectories
-    differ particle by particle (like the reference's MT vs ST runs) but the bulk must agree."""
+    """Statistical parity with the REFERENCE's own single-thread run of its default scene (golden dump): the coloured
+    sweep is a different, equally legitimate in-place order, so trajectories differ particle by particle (like the
+    reference's MT vs ST runs) but the bulk must agree - within the reference's own MT-vs-ST spread (envelope_lib;
+    all four volume scenes and K up to 256: tests/test_gpu_envelope.py)."""
+    import envelope_lib as E
+
     g = np.load(os.path.join(GOLDEN_DIR, "scene0.npz"))
     gpu = pkg.ParticleSimulation()
     gpu.LoadScenario(0, seed=1)
     assert_bits_equal(gpu.particles(), g["init"], "initial state equals the reference's")
     for _ in range(8):
         gpu.Update(DT)
-    a, b = gpu.particles(), g["state8"]
-    ke = lambda p: 0.5 * float((p[:, 6:8].astype(np.float64) ** 2).sum())
-    assert abs(ke(a) / ke(b) - 1.0) < 0.5
-    assert np.abs(a[:, 0:2].mean(0) - b[:, 0:2].mean(0)).max() < 2e-2   # centre of mass
-    assert abs(a[:, 8].mean() / b[:, 8].mean() - 1.0) < 0.05            # mean density
+    E.check_aggregates(E.load(), 0, 8, gpu.particles())
     gpu.close()
 
 
