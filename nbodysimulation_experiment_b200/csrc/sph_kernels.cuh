@@ -520,21 +520,38 @@ __global__ void __launch_bounds__(SPH_THREADS) scan_add_kernel(uint32_t *__restr
 // a quarter of the domain, so these three kernels build them sorted instead: one warp per (grid row, cx mod 3)
 // counts its occupied cells, one block turns the counts into list offsets (rows of equal colour in ascending
 // order), and the same warps write the cells behind their offset.  Deterministic as a side effect.
+//
+// LIGHT and HEAVY cells.  A cell's sweep is a serial chain over its particles, and the nine colours are a serial
+// chain over the cells of a neighbourhood: where a column of fluid compresses (cells with 40-80 particles and 400
+// candidates next to the usual 9 and 81) one warp per cell leaves the GPU waiting for nine heavy cells in a row.
+// The lists therefore come in two classes per colour: LIGHT cells (the 3x3 block fits one warp's staging area and its
+// work m x T is below `workHeavy`) are swept one warp per cell, HEAVY cells by a whole thread block per cell
+// (sweep_cell_team).  Same arithmetic, same bits (tests compare every kernel with the oracle).  The light list of a
+// colour grows from the front of its region of `colorList`, the heavy list from the back; colorCount[0..8] are the
+// light counts, colorCount[9..17] the heavy ones.  The class is decided once, in color_rows_count_kernel, which
+// leaves it in bit 31 of the cell's histogram word (cellCount is not read again after the scan).
 #define SPH_ROWLIST_WARPS 6 // two rows (x three column classes) per block
+#define SPH_CELL_HEAVY 0x80000000u
+
+struct SweepClass {
+	uint32_t capLight;  // a light cell's padded candidate count fits this (the per-warp staging capacity of the sweeps)
+	uint32_t workHeavy; // m x T from which a cell is heavy whatever its size
+};
 
 // Also resets the done flags of the one-launch sweep for this grid: 0 = occupied, not swept in any pass yet;
-// SPH_FLOW_EMPTY = nothing to wait for, ever.  (flow[0..1] are the ticket counters, the flags start at flow + 2.)
+// SPH_FLOW_EMPTY = nothing to wait for, ever.  (flow[0..3] are the ticket counters, the flags start at flow + 4.)
 #define SPH_FLOW_EMPTY 0xFFFFFFFFu
-#define SPH_FLOW_FLAGS 2u
-__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ rowColor,
+#define SPH_FLOW_FLAGS 4u
+__global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, SweepClass cls, uint32_t *__restrict__ cellCount,
+                                                                                const uint32_t *__restrict__ cellStart, uint32_t *__restrict__ rowColor,
                                                                                 uint32_t *__restrict__ flow) {
 	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
 	if (wid >= nRows * 3u) return;
 	const uint32_t row = wid / 3u, a = wid - row * 3u;
-	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
+	uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
 	uint32_t *flags = flow + SPH_FLOW_FLAGS + (size_t)row * (uint32_t)g.gx;
-	uint32_t n = 0;
+	uint32_t nLight = 0, nHeavy = 0;
 	for (uint32_t c0 = a + 3u * lane; c0 < (uint32_t)g.gx; c0 += 4u * 96u) { // four loads in flight per round trip
 		uint32_t v[4];
 #pragma unroll
@@ -544,21 +561,39 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kerne
 			const uint32_t cx = c0 + 96u * (uint32_t)u;
 			if (cx < (uint32_t)g.gx) {
 				flags[cx] = v[u] ? 0u : SPH_FLOW_EMPTY;
-				n += v[u] ? 1u : 0u;
+				if (v[u]) { // candidates of the 3x3 block, read off the prefix (only occupied cells pay for this)
+					const uint32_t x0 = cx ? cx - 1u : 0u, x1 = min(cx + 1u, (uint32_t)g.gx - 1u) + 1u;
+					uint32_t T = 0;
+#pragma unroll
+					for (int dr = -1; dr <= 1; ++dr) {
+						const int y = (int)row + dr;
+						if (y >= 0 && y < (int)nRows) T += cellStart[(uint32_t)y * (uint32_t)g.gx + x1] - cellStart[(uint32_t)y * (uint32_t)g.gx + x0];
+					}
+					const bool heavy = ((T + 31u) & ~31u) > cls.capLight || (unsigned long long)v[u] * T >= cls.workHeavy;
+					if (heavy) cc[cx] = v[u] | SPH_CELL_HEAVY;
+					nHeavy += heavy ? 1u : 0u;
+					nLight += heavy ? 0u : 1u;
+				}
 			}
 		}
 	}
-	n = warp_sum(n);
-	if (lane == 0) rowColor[wid] = n;
+	nLight = warp_sum(nLight);
+	nHeavy = warp_sum(nHeavy);
+	if (lane == 0) {
+		rowColor[wid] = nLight;
+		rowColor[nRows * 3u + wid] = nHeavy;
+	}
 }
 
-// nine warps, one per colour k = (row mod 3)*3 + a: exclusive scan of rowColor over that colour's rows, in place
-__global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount,
-                                                                 uint32_t *__restrict__ flow) {
-	const uint32_t k = threadIdx.x >> 5, lane = lane_id();
-	if (threadIdx.x < 2) flow[threadIdx.x] = 0u; // ticket counters of the next two passes over this grid
+// eighteen warps, one per (class, colour k = (row mod 3)*3 + a): exclusive scan of rowColor over that colour's rows, in place
+__global__ void __launch_bounds__(18 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount,
+                                                                  uint32_t *__restrict__ flow) {
+	const uint32_t kk = threadIdx.x >> 5, lane = lane_id();
+	if (threadIdx.x < 4) flow[threadIdx.x] = 0u; // ticket counters (light, heavy) of the next two passes over this grid
+	const uint32_t cls = kk / 9u, k = kk - cls * 9u;
 	const uint32_t b = k / 3u, a = k - b * 3u;
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
+	uint32_t *rc = rowColor + (size_t)cls * nRows * 3u;
 	const uint32_t r0 = (b + 3u - (uint32_t)g.rowLo % 3u) % 3u; // first local row whose global row is b mod 3
 	uint32_t running = 0;
 	for (uint32_t base = r0; base < nRows; base += 4u * 96u) { // four loads in flight per round trip
@@ -566,7 +601,7 @@ __global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uin
 #pragma unroll
 		for (int u = 0; u < 4; ++u) {
 			const uint32_t row = base + 96u * (uint32_t)u + 3u * lane;
-			v[u] = row < nRows ? rowColor[row * 3u + a] : 0u;
+			v[u] = row < nRows ? rc[row * 3u + a] : 0u;
 		}
 #pragma unroll
 		for (int u = 0; u < 4; ++u) {
@@ -577,11 +612,11 @@ __global__ void __launch_bounds__(9 * 32) color_rows_scan_kernel(GridDesc g, uin
 				const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
 				if ((int)lane >= o) inc += up;
 			}
-			if (row < nRows) rowColor[row * 3u + a] = running + inc - v[u];
+			if (row < nRows) rc[row * 3u + a] = running + inc - v[u];
 			running += __shfl_sync(0xffffffffu, inc, 31);
 		}
 	}
-	if (lane == 0) colorCount[k] = running;
+	if (lane == 0) colorCount[kk] = running;
 }
 
 __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, const uint32_t *__restrict__ rowColor,
@@ -593,7 +628,7 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel
 	const uint32_t k = ((row + (uint32_t)g.rowLo) % 3u) * 3u + a;
 	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
 	uint32_t *list = colorList + (size_t)k * listStride;
-	uint32_t at = rowColor[wid];
+	uint32_t at = rowColor[wid], atHeavy = rowColor[nRows * 3u + wid];
 	for (uint32_t c0 = a; c0 < (uint32_t)g.gx; c0 += 4u * 96u) { // warp-uniform trip count, four loads in flight per round trip
 		uint32_t v[4];
 #pragma unroll
@@ -604,12 +639,20 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel
 #pragma unroll
 		for (int u = 0; u < 4; ++u) {
 			const uint32_t cx = c0 + 96u * (uint32_t)u + 3u * lane;
-			const bool occ = v[u] != 0u;
-			const uint32_t mask = __ballot_sync(0xffffffffu, occ);
-			if (occ) list[at + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = row * (uint32_t)g.gx + cx;
+			const bool heavy = (v[u] & SPH_CELL_HEAVY) != 0u, light = v[u] != 0u && !heavy;
+			const uint32_t mask = __ballot_sync(0xffffffffu, light), maskH = __ballot_sync(0xffffffffu, heavy);
+			if (light) list[at + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = row * (uint32_t)g.gx + cx;
+			if (heavy) list[listStride - 1u - (atHeavy + (uint32_t)__popc(maskH & ((1u << lane) - 1u)))] = row * (uint32_t)g.gx + cx;
 			at += (uint32_t)__popc(mask);
+			atHeavy += (uint32_t)__popc(maskH);
 		}
 	}
+}
+
+// cell number idx of one colour: the light list from the front, then the heavy list from the back (the per-colour
+// kernels sweep both; the order inside a colour is free)
+__device__ __forceinline__ uint32_t colour_cell(const uint32_t *__restrict__ list, uint32_t listStride, uint32_t nLight, uint32_t idx) {
+	return idx < nLight ? list[idx] : list[listStride - 1u - (idx - nLight)];
 }
 
 // ---- phase 4c: drop each id at (cell start + arrival rank) ----------------------------------
@@ -953,11 +996,40 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 	}
 }
 
+// the 3x3 block of local cell c
+__device__ __forceinline__ SweepBlock sweep_block_of(const GridDesc &g, const uint32_t *__restrict__ cellStart, uint32_t c, int nRows) {
+	const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
+	const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
+	uint32_t lo[3], cnt[3];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		const int y = yl - 1 + r;
+		if (y < 0 || y >= nRows) {
+			lo[r] = 0;
+			cnt[r] = 0;
+		} else {
+			lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
+			cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
+		}
+	}
+	SweepBlock b;
+	b.lo0 = lo[0];
+	b.lo1 = lo[1];
+	b.lo2 = lo[2];
+	b.off1 = cnt[0];
+	b.off2 = cnt[0] + cnt[1];
+	b.T = b.off2 + cnt[2];
+	b.ownLo = cellStart[c];
+	b.m = cellStart[c + 1] - b.ownLo;
+	b.ownOff = b.off1 + (b.ownLo - lo[1]);
+	return b;
+}
+
 template <class M, int PASS>
 __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
-                                                                          const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
-                                                                          float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
-                                                                          Counters *__restrict__ ctr) {
+                                                                          const uint32_t *__restrict__ colorList, uint32_t listStride,
+                                                                          const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel,
+                                                                          const float2 *__restrict__ press, uint32_t cap, Counters *__restrict__ ctr) {
 	extern __shared__ __align__(16) unsigned char sweepSmem[];
 	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
 	unsigned char *mine = sweepSmem + (size_t)w * sweep_bytes_per_warp(cap, PASS);
@@ -966,34 +1038,11 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 	uint16_t *queueStaged = reinterpret_cast<uint16_t *>(sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1));
 	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
-	const uint32_t nList = *colorCount;
+	const uint32_t nLight = colorCount[0], nList = nLight + colorCount[9]; // this colour's light and heavy cells alike
 	const int nRows = g.rowHi - g.rowLo;
 	for (uint32_t idx = blockIdx.x * SPH_SWEEP_WARPS + w; idx < nList; idx += gridDim.x * SPH_SWEEP_WARPS) {
-		const uint32_t c = colorList[idx];
-		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
-		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
-		uint32_t lo[3], cnt[3];
-#pragma unroll
-		for (int r = 0; r < 3; ++r) {
-			const int y = yl - 1 + r;
-			if (y < 0 || y >= nRows) {
-				lo[r] = 0;
-				cnt[r] = 0;
-			} else {
-				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
-				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
-			}
-		}
-		SweepBlock b;
-		b.lo0 = lo[0];
-		b.lo1 = lo[1];
-		b.lo2 = lo[2];
-		b.off1 = cnt[0];
-		b.off2 = cnt[0] + cnt[1];
-		b.T = b.off2 + cnt[2];
-		b.ownLo = cellStart[c];
-		b.m = cellStart[c + 1] - b.ownLo;
-		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		const uint32_t c = colour_cell(colorList, listStride, nLight, idx);
+		const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
 		if (((b.T + 31u) & ~31u) <= cap) {
 			sweep_cell<M, PASS, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask);
 		} else if (b.T <= wideCap) {
@@ -1005,6 +1054,155 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 	}
 }
 
+// ---- the same sweep with a whole thread block per cell --------------------------------------------
+// One warp per cell leaves most of the GPU idle when a colour has fewer cells than the device has warp
+// slots (the reference's own scenes: 594 cells, 66 per colour), and the chain of a cell's particles is
+// strictly serial.  Here SPH_TEAM_WARPS warps share one cell: the candidate tests and the pair terms of
+// a particle are spread over the warps, the queue is assembled from per-trip ballots with a prefix sum,
+// and warp 0 folds the stored pair terms in queue order - the additions, their order and the lane
+// assignment are exactly those of color_sweep_kernel, so both kernels produce the same bits and the
+// host may pick either by load.  Used by color_sweep_team_kernel (nine launches, every cell) and for the
+// HEAVY cells of the one-launch sweep (color_sweep_flow_kernel).
+#define SPH_TEAM_WARPS 8
+#define SPH_TEAM_MAX_CAP 2048u // two trips per lane in the prefix over the trips' hit counts
+__host__ __device__ inline uint32_t team_smem_bytes(uint32_t cap, int pass) {
+	return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) /* sPos (+ sVel) */ + cap * 2u /* queue */ + cap * 8u /* pair terms */ + (cap / 32u + 2u) * 4u /* ballots */;
+}
+// the largest staging capacity (multiple of 32, <= SPH_TEAM_MAX_CAP) a team can run in `bytes` of shared memory
+__host__ __device__ inline uint32_t team_capacity(uint32_t bytes, int pass) {
+	const uint32_t per32 = 32u * (8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) + 2u + 8u) + 4u;
+	const uint32_t cap = bytes > 8u ? ((bytes - 8u) / per32) * 32u : 0u;
+	return cap < SPH_TEAM_MAX_CAP ? cap : SPH_TEAM_MAX_CAP;
+}
+
+// One cell, one thread block of SPH_TEAM_WARPS warps (all threads call this; block barriers inside).
+// COHERENT as in sweep_cell: the staging loads bypass L1.
+template <class M, int PASS, bool COHERENT>
+__device__ __forceinline__ void sweep_cell_team(const PairParams &k, const SweepBlock &b, float2 *pos, float2 *vel, const float2 *__restrict__ press,
+                                                unsigned char *smem, uint32_t cap, Counters *__restrict__ ctr) {
+	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+	float2 *sPos = reinterpret_cast<float2 *>(smem);
+	float2 *sVel = sPos + cap; // viscosity only
+	float2 *sTerm = sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1);
+	uint16_t *queue = reinterpret_cast<uint16_t *>(sTerm + cap);
+	uint32_t *tripMask = reinterpret_cast<uint32_t *>(queue + cap);
+	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
+	const uint32_t Tpad = (b.T + 31u) & ~31u, nTrips = Tpad >> 5;
+	if (Tpad > cap) { // too large to stage: warp 0 takes the L2 path of the one-warp kernel (same arithmetic)
+		if (w == 0) {
+			const uint32_t wide = team_smem_bytes(cap, PASS) / 2u;
+			if (b.T <= wide) sweep_cell<M, PASS, false, COHERENT>(k, b, pos, vel, press, sPos, sVel, reinterpret_cast<uint16_t *>(smem), lane, ltMask);
+			else if (lane == 0) atomicOr(&ctr->overflow, 4u);
+		}
+		__syncthreads();
+		return;
+	}
+	for (uint32_t t = threadIdx.x; t < Tpad; t += SPH_TEAM_WARPS * 32) {
+		if (t < b.T) {
+			const uint32_t j = b.gidx(t);
+			sPos[t] = COHERENT ? __ldcg(&pos[j]) : pos[j];
+			if (PASS == SWEEP_VISCOSITY) sVel[t] = COHERENT ? __ldcg(&vel[j]) : vel[j];
+		} else {
+			sPos[t] = make_float2(3.0e18f, 3.0e18f);
+		}
+	}
+	__syncthreads();
+	for (uint32_t kBase = 0; kBase < b.m; kBase += 32) {
+		float2 myPress = make_float2(0.0f, 0.0f);
+		if (PASS == SWEEP_DELTA && kBase + lane < b.m) myPress = press[b.ownLo + kBase + lane];
+		const uint32_t kEnd = min(b.m - kBase, 32u);
+		for (uint32_t kk = 0; kk < kEnd; ++kk) {
+			const uint32_t si = b.ownOff + kBase + kk;
+			const float2 xi = sPos[si];
+			float2 vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
+			if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
+			if (PASS == SWEEP_DELTA) {
+				ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
+				ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
+			}
+			// stage 1a: every warp tests its share of the 32-candidate trips
+			for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
+				const float2 xj = sPos[tr * 32u + lane];
+				const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
+				const uint32_t mask = __ballot_sync(0xffffffffu, M::dot2(rx, rx, ry, ry) < k.h2);
+				if (lane == 0) tripMask[tr] = mask;
+			}
+			__syncthreads();
+			// stage 1b: exclusive prefix of the trips' hit counts (every warp redundantly; a lane looks after trips
+			// `lane` and `lane + 32`: cap <= 2048), then the queue in candidate order
+			const uint32_t myMask0 = lane < nTrips ? tripMask[lane] : 0u, myMask1 = lane + 32u < nTrips ? tripMask[lane + 32u] : 0u;
+			uint32_t incl0 = (uint32_t)__popc(myMask0), incl1 = (uint32_t)__popc(myMask1);
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t up0 = __shfl_up_sync(0xffffffffu, incl0, o), up1 = __shfl_up_sync(0xffffffffu, incl1, o);
+				if ((int)lane >= o) {
+					incl0 += up0;
+					incl1 += up1;
+				}
+			}
+			const uint32_t nHit0 = __shfl_sync(0xffffffffu, incl0, 31);
+			const uint32_t nHit = nHit0 + __shfl_sync(0xffffffffu, incl1, 31);
+			const uint32_t excl0 = incl0 - (uint32_t)__popc(myMask0), excl1 = nHit0 + incl1 - (uint32_t)__popc(myMask1);
+			for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
+				const uint32_t mask = tr < 32u ? __shfl_sync(0xffffffffu, myMask0, (int)tr) : __shfl_sync(0xffffffffu, myMask1, (int)(tr - 32u));
+				const uint32_t base = tr < 32u ? __shfl_sync(0xffffffffu, excl0, (int)tr) : __shfl_sync(0xffffffffu, excl1, (int)(tr - 32u));
+				if (mask & (1u << lane)) queue[base + (uint32_t)__popc(mask & ltMask)] = (uint16_t)(tr * 32u + lane);
+			}
+			__syncthreads();
+			// stage 2: pair terms, partner updated at once; the terms are kept for warp 0
+			for (uint32_t q = w * 32u + lane; q < nHit; q += SPH_TEAM_WARPS * 32) {
+				const uint32_t t = queue[q];
+				bool hit;
+				float2 hlf;
+				if (PASS == SWEEP_DELTA) {
+					const float2 xj = sPos[t];
+					hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit);
+					sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+				} else {
+					const float2 vj = sVel[t];
+					hlf = sweep_viscosity_term<M, false>(k, xi, vi, sPos[t], vj, hit);
+					if (hit) sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+					else hlf = make_float2(0.0f, 0.0f); // x - (+0) == x bit for bit
+				}
+				sTerm[q] = hlf;
+			}
+			__syncthreads();
+			// the particle's own change: warp 0 repeats the one-warp kernel's additions in its order
+			if (w == 0) {
+				float ax = 0.0f, ay = 0.0f;
+				for (uint32_t q = lane; q < nHit; q += 32) {
+					const float2 hlf = sTerm[q];
+					ax = __fsub_rn(ax, hlf.x);
+					ay = __fsub_rn(ay, hlf.y);
+				}
+				const float2 own = butterfly_sum2_lane0(ax, ay, lane);
+				if (lane == 0) {
+					float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
+					*slot = make_float2(__fadd_rn(own.x, slot->x), __fadd_rn(own.y, slot->y));
+				}
+			}
+			__syncthreads();
+		}
+	}
+	for (uint32_t t = threadIdx.x; t < b.T; t += SPH_TEAM_WARPS * 32) state[b.gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
+	__syncthreads();
+}
+
+template <class M, int PASS>
+__global__ void __launch_bounds__(SPH_TEAM_WARPS * 32) color_sweep_team_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
+                                                                               const uint32_t *__restrict__ colorList, uint32_t listStride,
+                                                                               const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel,
+                                                                               const float2 *__restrict__ press, uint32_t cap, Counters *__restrict__ ctr) {
+	extern __shared__ __align__(16) unsigned char teamSmem[];
+	const uint32_t nLight = colorCount[0], nList = nLight + colorCount[9];
+	const int nRows = g.rowHi - g.rowLo;
+	for (uint32_t idx = blockIdx.x; idx < nList; idx += gridDim.x) {
+		const uint32_t c = colour_cell(colorList, listStride, nLight, idx);
+		const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
+		sweep_cell_team<M, PASS, false>(k, b, pos, vel, press, teamSmem, cap, ctr);
+	}
+}
+
 // ---- the nine colours in ONE launch: dependency-driven sweep --------------------------------------
 // Nine launches per pass leave eighteen tails per step in which most of the GPU waits for the last
 // few cells of a colour.  Here the occupied cells of all colours form one queue (colour 0's list,
@@ -1013,12 +1211,18 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 // within two rows/columns - has finished; cells of a higher colour inside that range wait for it by
 // the same rule.  Cells that are further apart never touch the same particles.  Every cell therefore
 // reads exactly the state it reads in the nine-launch version and the results are bit-identical.
-// Deadlock-free: tickets are handed out in queue order and a warp works its tickets in order, so the
-// unfinished cell with the lowest ticket only waits for finished ones and its warp is running it.
-// `flow[0..1]` are ticket counters and `flow[2 + cell]` the done flags, (re)initialised with every grid build
+// `flow[0..3]` are ticket counters and `flow[4 + cell]` the done flags, (re)initialised with every grid build
 // (color_rows_count_kernel).  Loads of particle state bypass L1 (another SM may have just rewritten it).
-#define SPH_FLOW_WARPS 4
-#define SPH_FLOW_MIN_BLOCKS 10 // 48 registers: at 40 (12 blocks) ptxas rematerialises addresses inside the pair loops, +26 % instructions (ncu, r1b)
+//
+// Two queues: the LIGHT cells (one warp per cell) and the HEAVY cells (one block per cell, sweep_cell_team), both in
+// colour-major, row-major order.  The first `teams` blocks of the grid (as many as the fullest colour has heavy cells,
+// at most half the grid) drain the heavy queue as teams and then join the others on the light queue.
+// Deadlock-free: tickets of either queue are handed out in queue order and a worker takes its tickets in order, so the
+// unfinished cell that comes first in (colour, row, column) order only waits for finished cells, all cells ahead of it
+// in its own queue are finished, i.e. their workers have moved on and one of them holds its ticket or draws it next;
+// there is always at least one worker per non-empty queue (the host launches at least two blocks, all resident).
+#define SPH_FLOW_WARPS 8
+#define SPH_FLOW_MIN_BLOCKS 5 // 48 registers: at 40 ptxas rematerialises addresses inside the pair loops, +26 % instructions (ncu, r1b)
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 	uint32_t v;
@@ -1027,29 +1231,97 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// The lower-colour cells of the 5x5 neighbourhood of local cell c must be done (empty ones always are): lane l looks
+// after cell (l%5-2, l/5-2).  Returns the flag this lane still has to wait for (nullptr: none).
+__device__ __forceinline__ const uint32_t *flow_pending_flag(const GridDesc &g, const uint32_t *flags, uint32_t c, int nRows, uint32_t epoch, uint32_t lane) {
+	const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
+	const int color = (int)(((uint32_t)(yl + g.rowLo) % 3u) * 3u + (uint32_t)cx % 3u);
+	const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
+	if (lane < 25u && lane != 12u && nx >= 0 && nx < g.gx && ny >= 0 && ny < nRows) {
+		const int ncolor = (int)(((uint32_t)(ny + g.rowLo) % 3u) * 3u + (uint32_t)nx % 3u);
+		const uint32_t *f = flags + ((uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx);
+		if (ncolor < color && ld_acquire_gpu(f) < epoch) return f;
+	}
+	return nullptr;
+}
+
 template <class M, int PASS>
 __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
     color_sweep_flow_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ colorList, uint32_t listStride,
                             const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
-                            Counters *__restrict__ ctr, uint32_t *flow, uint32_t epoch) {
+                            Counters *__restrict__ ctr, uint32_t *flow, uint32_t epoch, uint32_t maxTeams) {
 	extern __shared__ __align__(16) unsigned char sweepSmem[];
 	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+	const int nRows = g.rowHi - g.rowLo;
+	__shared__ uint32_t counts[18]; // cells per class and colour: shared memory, registers would cost occupancy
+	__shared__ uint32_t teamTicket;
+	if (threadIdx.x < 18) counts[threadIdx.x] = colorCount[threadIdx.x];
+	__syncthreads();
+	// `epoch` counts the sweeps over this grid (1 = the displacement pass right after the grid build, 2 = the next
+	// step's viscosity pass, more only through sph_run_pass): a cell is done once its flag >= epoch, so the flags
+	// need no reset between passes; passes alternate between two pairs of ticket counters and zero the other pair.
+	uint32_t *tickets = flow + (epoch & 1u);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		flow[(epoch + 1u) & 1u] = 0u;
+		flow[2u + ((epoch + 1u) & 1u)] = 0u;
+	}
+	uint32_t *flags = flow + SPH_FLOW_FLAGS;
+	// queue position -> cell (SPH_KEY_NONE past the end); cls 0 = light (front of a colour's region), 1 = heavy (back)
+	auto cell_of_ticket = [&](uint32_t t, uint32_t cls) -> uint32_t {
+		uint32_t seen = 0, at = 0xffffffffu, base = 0;
+#pragma unroll
+		for (int cc = 0; cc < 9; ++cc) {
+			const uint32_t n = counts[cls * 9u + (uint32_t)cc];
+			if (t >= seen && t < seen + n) {
+				at = t - seen;
+				base = (uint32_t)cc * listStride;
+			}
+			seen += n;
+		}
+		if (at == 0xffffffffu) return SPH_KEY_NONE;
+		return __ldg(&colorList[(size_t)base + (cls ? listStride - 1u - at : at)]);
+	};
+
+	// ---- heavy cells: the first `teams` blocks, one block per cell --------------------------------------------
+	{
+		uint32_t mostHeavy = 0;
+#pragma unroll
+		for (int cc = 0; cc < 9; ++cc) mostHeavy = max(mostHeavy, counts[9 + cc]);
+		const uint32_t teams = mostHeavy ? max(1u, min(mostHeavy, min(maxTeams, gridDim.x / 2u))) : 0u;
+		if (blockIdx.x < teams) {
+			const uint32_t capTeam = team_capacity(SPH_FLOW_WARPS * sweep_bytes_per_warp(cap, PASS), PASS);
+			uint32_t *teamTickets = flow + 2u + (epoch & 1u);
+			for (;;) {
+				if (threadIdx.x == 0) teamTicket = atomicAdd(teamTickets, 1u);
+				__syncthreads();
+				const uint32_t c = cell_of_ticket(teamTicket, 1u);
+				if (c == SPH_KEY_NONE) break; // (uniform: every thread read the same ticket)
+				const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
+				if (w == 0) {
+					const uint32_t *flag = flow_pending_flag(g, flags, c, nRows, epoch, lane);
+					while (!__all_sync(0xffffffffu, flag == nullptr)) {
+						__nanosleep(100);
+						if (flag && ld_acquire_gpu(flag) >= epoch) flag = nullptr;
+					}
+				}
+				__syncthreads(); // also: nobody draws the next ticket before everybody has read this one
+				sweep_cell_team<M, PASS, true>(k, b, pos, vel, press, sweepSmem, capTeam, ctr);
+				// done: every thread's write-back is ordered before the barrier inside sweep_cell_team, one thread releases
+				__threadfence();
+				__syncthreads();
+				if (threadIdx.x == 0) st_release_gpu(flags + c, epoch);
+			}
+			__syncthreads();
+		}
+	}
+
+	// ---- light cells: one warp per cell -------------------------------------------------------------------------
 	unsigned char *mine = sweepSmem + (size_t)w * sweep_bytes_per_warp(cap, PASS);
 	float2 *sPos = reinterpret_cast<float2 *>(mine);
 	float2 *sVel = sPos + cap; // viscosity only
 	uint16_t *queueStaged = reinterpret_cast<uint16_t *>(sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1));
 	uint16_t *queueWide = reinterpret_cast<uint16_t *>(mine);
 	const uint32_t wideCap = sweep_queue_capacity(cap, PASS);
-	const int nRows = g.rowHi - g.rowLo;
-	__shared__ uint32_t counts[9]; // cells per colour: shared memory, nine registers per thread would cost occupancy
-	if (threadIdx.x < 9) counts[threadIdx.x] = colorCount[threadIdx.x];
-	__syncthreads();
-	// `epoch` counts the sweeps over this grid (1 = the displacement pass right after the grid build, 2 = the next
-	// step's viscosity pass, more only through sph_run_pass): a cell is done once its flag >= epoch, so the flags
-	// need no reset between passes; passes alternate between two ticket counters and zero the other one.
-	uint32_t *tickets = flow + (epoch & 1u);
-	if (blockIdx.x == 0 && threadIdx.x == 0) flow[(epoch + 1u) & 1u] = 0u;
-	uint32_t *flags = flow + SPH_FLOW_FLAGS;
 	// The next ticket is drawn when a cell's arithmetic is over, just before its write-back, and read after the
 	// done flag is up: the atomic's round trip overlaps the stores'.  Drawing it any earlier would hide it as well
 	// but park cells: every ticket a warp holds without working on it widens the window of cells in flight, and
@@ -1063,58 +1335,11 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		if (lane < 2u) asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(tickets + (lane == 0u ? 0u : decoy)) : "memory");
 		return t; // valid in lane 0
 	};
-	// queue position -> cell (SPH_KEY_NONE past the end)
-	auto cell_of_ticket = [&](uint32_t t) -> uint32_t {
-		uint32_t seen = 0, at = 0xffffffffu, base = 0;
-#pragma unroll
-		for (int cc = 0; cc < 9; ++cc) {
-			if (t >= seen && t < seen + counts[cc]) {
-				at = t - seen;
-				base = (uint32_t)cc * listStride;
-			}
-			seen += counts[cc];
-		}
-		return at == 0xffffffffu ? SPH_KEY_NONE : __ldg(&colorList[(size_t)base + at]);
-	};
-	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0));
+	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0), 0u);
 	while (c != SPH_KEY_NONE) {
-		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
-		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
-		uint32_t lo[3], cnt[3];
-#pragma unroll
-		for (int r = 0; r < 3; ++r) {
-			const int y = yl - 1 + r;
-			if (y < 0 || y >= nRows) {
-				lo[r] = 0;
-				cnt[r] = 0;
-			} else {
-				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
-				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
-			}
-		}
-		const uint32_t ownLo = cellStart[c], ownHi = cellStart[c + 1];
-		// The lower-colour cells of the 5x5 neighbourhood must be done (empty ones always are): lane l looks after cell
-		// (l%5-2, l/5-2).  The flag is fetched together with the loads above: one round trip to L2 for all of them.
-		const uint32_t *flag = nullptr;
-		{
-			const int color = (int)(((uint32_t)(yl + g.rowLo) % 3u) * 3u + (uint32_t)cx % 3u);
-			const int nx = cx + (int)(lane % 5u) - 2, ny = yl + (int)(lane / 5u) - 2;
-			if (lane < 25u && lane != 12u && nx >= 0 && nx < g.gx && ny >= 0 && ny < nRows) {
-				const int ncolor = (int)(((uint32_t)(ny + g.rowLo) % 3u) * 3u + (uint32_t)nx % 3u);
-				const uint32_t *f = flags + ((uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx);
-				if (ncolor < color && ld_acquire_gpu(f) < epoch) flag = f;
-			}
-		}
-		SweepBlock b;
-		b.lo0 = lo[0];
-		b.lo1 = lo[1];
-		b.lo2 = lo[2];
-		b.off1 = cnt[0];
-		b.off2 = cnt[0] + cnt[1];
-		b.T = b.off2 + cnt[2];
-		b.ownLo = ownLo;
-		b.m = ownHi - ownLo;
-		b.ownOff = b.off1 + (b.ownLo - lo[1]);
+		const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
+		// (the flags are fetched together with the loads above: one round trip to L2 for all of them)
+		const uint32_t *flag = flow_pending_flag(g, flags, c, nRows, epoch, lane);
 		while (!__all_sync(0xffffffffu, flag == nullptr)) {
 			__nanosleep(100);
 			if (flag && ld_acquire_gpu(flag) >= epoch) flag = nullptr;
@@ -1124,7 +1349,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		auto draw_next = [&]() { nextTicket = draw_ticket(); };
 		if (((b.T + 31u) & ~31u) <= cap) {
 			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask, draw_next);
-		} else if (b.T <= wideCap) {
+		} else if (b.T <= wideCap) { // (only when the lists were classified for a larger staging capacity than this launch has)
 			sweep_cell<M, PASS, false, true>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask, draw_next);
 		} else { // denser than anything the queue can hold: report, leave the cell alone
 			if (lane == 0) atomicOr(&ctr->overflow, 4u);
@@ -1133,158 +1358,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		// done: one lane releases for the warp (the __syncwarp orders every lane's write-back before it)
 		__syncwarp();
 		if (lane == 0) st_release_gpu(flags + c, epoch);
-		c = cell_of_ticket(__shfl_sync(0xffffffffu, nextTicket, 0));
-	}
-}
-
-// ---- the same sweep with a whole thread block per cell --------------------------------------------
-// One warp per cell leaves most of the GPU idle when a colour has fewer cells than the device has warp
-// slots (the reference's own scenes: 594 cells, 66 per colour), and the chain of a cell's particles is
-// strictly serial.  Here SPH_TEAM_WARPS warps share one cell: the candidate tests and the pair terms of
-// a particle are spread over the warps, the queue is assembled from per-trip ballots with a prefix sum,
-// and warp 0 folds the stored pair terms in queue order - the additions, their order and the lane
-// assignment are exactly those of color_sweep_kernel, so both kernels produce the same bits and the
-// host may pick either by load.
-#define SPH_TEAM_WARPS 8
-__host__ __device__ inline uint32_t team_smem_bytes(uint32_t cap, int pass) {
-	return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) /* sPos (+ sVel) */ + cap * 2u /* queue */ + cap * 8u /* pair terms */ + (cap / 32u + 2u) * 4u /* ballots */;
-}
-
-template <class M, int PASS>
-__global__ void __launch_bounds__(SPH_TEAM_WARPS * 32) color_sweep_team_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart,
-                                                                               const uint32_t *__restrict__ colorList, const uint32_t *__restrict__ colorCount,
-                                                                               float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
-                                                                               Counters *__restrict__ ctr) {
-	extern __shared__ __align__(16) unsigned char teamSmem[];
-	const uint32_t lane = lane_id(), w = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
-	float2 *sPos = reinterpret_cast<float2 *>(teamSmem);
-	float2 *sVel = sPos + cap; // viscosity only
-	float2 *sTerm = sPos + cap * (PASS == SWEEP_VISCOSITY ? 2 : 1);
-	uint16_t *queue = reinterpret_cast<uint16_t *>(sTerm + cap);
-	uint32_t *tripMask = reinterpret_cast<uint32_t *>(queue + cap);
-	const uint32_t nList = *colorCount;
-	const int nRows = g.rowHi - g.rowLo;
-	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
-	for (uint32_t idx = blockIdx.x; idx < nList; idx += gridDim.x) {
-		const uint32_t c = colorList[idx];
-		const int yl = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)yl * (uint32_t)g.gx);
-		const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
-		uint32_t lo[3], cnt[3];
-#pragma unroll
-		for (int r = 0; r < 3; ++r) {
-			const int y = yl - 1 + r;
-			if (y < 0 || y >= nRows) {
-				lo[r] = 0;
-				cnt[r] = 0;
-			} else {
-				lo[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x0];
-				cnt[r] = cellStart[(uint32_t)y * (uint32_t)g.gx + (uint32_t)x1 + 1u] - lo[r];
-			}
-		}
-		SweepBlock b;
-		b.lo0 = lo[0];
-		b.lo1 = lo[1];
-		b.lo2 = lo[2];
-		b.off1 = cnt[0];
-		b.off2 = cnt[0] + cnt[1];
-		b.T = b.off2 + cnt[2];
-		b.ownLo = cellStart[c];
-		b.m = cellStart[c + 1] - b.ownLo;
-		b.ownOff = b.off1 + (b.ownLo - lo[1]);
-		const uint32_t Tpad = (b.T + 31u) & ~31u, nTrips = Tpad >> 5;
-		if (Tpad > cap) { // too large to stage: warp 0 takes the L2 path of the one-warp kernel (same arithmetic)
-			if (w == 0) {
-				const uint32_t wide = team_smem_bytes(cap, PASS) / 2u;
-				if (b.T <= wide) sweep_cell<M, PASS, false>(k, b, pos, vel, press, sPos, sVel, reinterpret_cast<uint16_t *>(teamSmem), lane, ltMask);
-				else if (lane == 0) atomicOr(&ctr->overflow, 4u);
-			}
-			__syncthreads();
-			continue;
-		}
-		for (uint32_t t = threadIdx.x; t < Tpad; t += SPH_TEAM_WARPS * 32) {
-			if (t < b.T) {
-				const uint32_t j = b.gidx(t);
-				sPos[t] = pos[j];
-				if (PASS == SWEEP_VISCOSITY) sVel[t] = vel[j];
-			} else {
-				sPos[t] = make_float2(3.0e18f, 3.0e18f);
-			}
-		}
-		__syncthreads();
-		for (uint32_t kBase = 0; kBase < b.m; kBase += 32) {
-			float2 myPress = make_float2(0.0f, 0.0f);
-			if (PASS == SWEEP_DELTA && kBase + lane < b.m) myPress = press[b.ownLo + kBase + lane];
-			const uint32_t kEnd = min(b.m - kBase, 32u);
-			for (uint32_t kk = 0; kk < kEnd; ++kk) {
-				const uint32_t si = b.ownOff + kBase + kk;
-				const float2 xi = sPos[si];
-				float2 vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
-				if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
-				if (PASS == SWEEP_DELTA) {
-					ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
-					ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
-				}
-				// stage 1a: every warp tests its share of the 32-candidate trips
-				for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
-					const float2 xj = sPos[tr * 32u + lane];
-					const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-					const uint32_t mask = __ballot_sync(0xffffffffu, M::dot2(rx, rx, ry, ry) < k.h2);
-					if (lane == 0) tripMask[tr] = mask;
-				}
-				__syncthreads();
-				// stage 1b: exclusive prefix of the trips' hit counts (every warp redundantly), then the queue in candidate order
-				const uint32_t myMask = lane < nTrips ? tripMask[lane] : 0u; // cap <= 1024: at most 32 trips
-				uint32_t incl = (uint32_t)__popc(myMask);
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-					if ((int)lane >= o) incl += up;
-				}
-				const uint32_t nHit = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t excl = incl - (uint32_t)__popc(myMask);
-				for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
-					const uint32_t mask = __shfl_sync(0xffffffffu, myMask, (int)tr);
-					const uint32_t base = __shfl_sync(0xffffffffu, excl, (int)tr);
-					if (mask & (1u << lane)) queue[base + (uint32_t)__popc(mask & ltMask)] = (uint16_t)(tr * 32u + lane);
-				}
-				__syncthreads();
-				// stage 2: pair terms, partner updated at once; the terms are kept for warp 0
-				for (uint32_t q = w * 32u + lane; q < nHit; q += SPH_TEAM_WARPS * 32) {
-					const uint32_t t = queue[q];
-					bool hit;
-					float2 hlf;
-					if (PASS == SWEEP_DELTA) {
-						const float2 xj = sPos[t];
-						hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit);
-						sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
-					} else {
-						const float2 vj = sVel[t];
-						hlf = sweep_viscosity_term<M, false>(k, xi, vi, sPos[t], vj, hit);
-						if (hit) sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
-						else hlf = make_float2(0.0f, 0.0f); // x - (+0) == x bit for bit
-					}
-					sTerm[q] = hlf;
-				}
-				__syncthreads();
-				// the particle's own change: warp 0 repeats the one-warp kernel's additions in its order
-				if (w == 0) {
-					float ax = 0.0f, ay = 0.0f;
-					for (uint32_t q = lane; q < nHit; q += 32) {
-						const float2 hlf = sTerm[q];
-						ax = __fsub_rn(ax, hlf.x);
-						ay = __fsub_rn(ay, hlf.y);
-					}
-					const float2 own = butterfly_sum2_lane0(ax, ay, lane);
-					if (lane == 0) {
-						float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
-						*slot = make_float2(__fadd_rn(own.x, slot->x), __fadd_rn(own.y, slot->y));
-					}
-				}
-				__syncthreads();
-			}
-		}
-		for (uint32_t t = threadIdx.x; t < b.T; t += SPH_TEAM_WARPS * 32) state[b.gidx(t)] = (PASS == SWEEP_DELTA) ? sPos[t] : sVel[t];
-		__syncthreads();
+		c = cell_of_ticket(__shfl_sync(0xffffffffu, nextTicket, 0), 0u);
 	}
 }
 

@@ -107,7 +107,7 @@ enum Phase { PH_INTEGRATE, PH_VISCOSITY, PH_PREDICT, PH_SCAN, PH_REORDER, PH_DEN
 static_assert(PH_COUNT == SPH_NUM_PHASES, "phase list");
 
 struct StepGraphKey {
-	uint32_t parity, sweepCap, nb, nbodies, haloMsgRecords, parts, flowEpoch;
+	uint32_t parity, sweepCap, gridSweepCap, workHeavy, nb, nbodies, haloMsgRecords, parts, flowEpoch;
 	uint32_t gridGen; // bumped whenever the grid description or the cell arrays change (configure_strip, apply_retarget)
 	float2 force;
 	PairParams k;
@@ -146,8 +146,13 @@ struct SphSim {
 	uint32_t *rowColor = nullptr;  // occupied cells per (local row, cx mod 3), then their offsets in the colour lists
 	uint32_t *sweepFlow = nullptr; // [0..1] ticket counters, [2 + cell] done flags of the one-launch sweep (color_sweep_flow_kernel), then decoy words
 	uint32_t flowEpoch = 0;        // sweeps launched over the current grid (the flags count passes, see color_sweep_flow_kernel)
-	uint32_t listStride = 0, sweepCap = 512;
-	bool sweepAdaptive = true;       // pick the staging capacity from the candidate-list maximum of recent steps
+	uint32_t listStride = 0, sweepCap = 256;
+	uint32_t gridSweepCap = 256;     // the staging capacity the current grid's lists were classified for (light cells fit it)
+	uint32_t workHeavy = 6000;       // m x T from which a cell is swept by a whole block (SweepClass)
+	float heavyFactor = 6.0f;        // ... as a multiple of the average m x T
+	uint32_t teamDiv = 2;            // at most 1/teamDiv of the sweep's blocks work as teams
+	float capAvg = 0.0f;             // candidates per particle the adaptive capacity was last chosen for
+	bool sweepAdaptive = true;       // pick the staging capacity from the candidates per particle of recent steps
 	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
 	cudaEvent_t lagEvent = nullptr;
 	bool lagPending = false;
@@ -527,8 +532,11 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
 	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) { // occupied cells per colour, each list in row-major order
 		const unsigned rowWarps = (unsigned)(g.rowHi - g.rowLo) * 3u, rowBlocks = (rowWarps + SPH_ROWLIST_WARPS - 1) / SPH_ROWLIST_WARPS;
-		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->sweepFlow);
-		color_rows_scan_kernel<<<1, 9 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount, s->sweepFlow);
+		// light / heavy split of the lists (sph_kernels.cuh, "LIGHT and HEAVY cells"): by this grid's staging capacity
+		s->gridSweepCap = s->sweepCap;
+		const SweepClass cls = { s->sweepCap, s->workHeavy };
+		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, cls, s->cellCount, s->cellStart, s->rowColor, s->sweepFlow);
+		color_rows_scan_kernel<<<1, 18 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount, s->sweepFlow);
 		s->flowEpoch = 0; // the done flags are fresh: the next sweep over this grid is its first
 		color_rows_fill_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->colorList, s->listStride);
 	}
@@ -603,12 +611,17 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 	const bool flow = !team && !(s->cfg.flags & SPH_FLAG_SWEEP_WARP);
 	if (flow) {
 		// persistent: as many blocks as are resident at once (more would only draw a ticket and leave)
-		const size_t smem = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
-		const int occBlocks = std::max(1, flowBlocksPerSM[std::min(96u, (s->sweepCap + 31u) / 32u)]);
+		// (the lists of the grid being swept were classified for gridSweepCap: never launch with less, or its light
+		// cells would not fit their warp's staging area and take the slow path through L2)
+		const uint32_t cap = std::max(s->sweepCap, s->gridSweepCap);
+		const size_t smem = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(cap, PASS);
+		const int occBlocks = std::max(1, flowBlocksPerSM[std::min(96u, (cap + 31u) / 32u)]);
 		const uint64_t want = (9 * cells + SPH_FLOW_WARPS - 1) / SPH_FLOW_WARPS;
-		const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
+		// at least two blocks: heavy cells are swept by the first blocks of the grid as teams, the others must be there for the light ones
+		const unsigned blocks = (unsigned)std::max<uint64_t>(2, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
 		color_sweep_flow_kernel<M, PASS><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
-		                                                                                 s->vel.in(), s->press.in(), s->sweepCap, s->dCtr, s->sweepFlow, ++s->flowEpoch);
+		                                                                                 s->vel.in(), s->press.in(), cap, s->dCtr, s->sweepFlow, ++s->flowEpoch,
+		                                                                                 std::max(1u, blocks / s->teamDiv));
 		return;
 	}
 	for (int color = 0; color < 9; ++color) {
@@ -616,12 +629,12 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 		if (team) {
 			const uint32_t cap = std::min(s->sweepCap, 1024u);
 			const unsigned blocks = (unsigned)std::min<uint64_t>(cells, 148u * 16u);
-			color_sweep_team_kernel<M, PASS><<<blocks, SPH_TEAM_WARPS * 32, team_smem_bytes(cap, PASS), s->stream>>>(s->grid, k, s->cellStart, list, s->colorCount + color,
+			color_sweep_team_kernel<M, PASS><<<blocks, SPH_TEAM_WARPS * 32, team_smem_bytes(cap, PASS), s->stream>>>(s->grid, k, s->cellStart, list, s->listStride, s->colorCount + color,
 			                                                                                               s->pos.in(), s->vel.in(), s->press.in(), cap, s->dCtr);
 		} else {
 			const size_t smem = (size_t)SPH_SWEEP_WARPS * sweep_bytes_per_warp(s->sweepCap, PASS);
 			const unsigned blocks = (unsigned)std::min<uint64_t>((cells + SPH_SWEEP_WARPS - 1) / SPH_SWEEP_WARPS, 148u * 64u);
-			color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, list, s->colorCount + color, s->pos.in(), s->vel.in(),
+			color_sweep_kernel<M, PASS><<<blocks, SPH_SWEEP_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, list, s->listStride, s->colorCount + color, s->pos.in(), s->vel.in(),
 			                                                                             s->press.in(), s->sweepCap, s->dCtr);
 		}
 	}
@@ -684,12 +697,12 @@ int configure_strip(SphSim *s, int ownLo, int ownHi) {
 	CU(s, cudaMalloc(&s->tileSums, ((allocCells + SPH_SCAN_TILE - 1) / SPH_SCAN_TILE + 1) * sizeof(uint32_t)));
 	s->listStride = (uint32_t)((g.gx + 2) / 3) * (uint32_t)((allocRows + 2) / 3 + 1);
 	CU(s, cudaMalloc(&s->colorList, (size_t)9 * s->listStride * sizeof(uint32_t)));
-	CU(s, cudaMalloc(&s->sweepFlow, (allocCells + 2 + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
-	CU(s, cudaMemset(s->sweepFlow, 0xFF, (allocCells + 2 + 65536) * sizeof(uint32_t))); // no grid yet: every cell empty
-	CU(s, cudaMemset(s->sweepFlow, 0, 2 * sizeof(uint32_t)));
-	if (s->colorCount) CU(s, cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->sweepFlow, (allocCells + SPH_FLOW_FLAGS + 65536) * sizeof(uint32_t))); // + one decoy word per resident warp (color_sweep_flow_kernel)
+	CU(s, cudaMemset(s->sweepFlow, 0xFF, (allocCells + SPH_FLOW_FLAGS + 65536) * sizeof(uint32_t))); // no grid yet: every cell empty
+	CU(s, cudaMemset(s->sweepFlow, 0, SPH_FLOW_FLAGS * sizeof(uint32_t)));
+	if (s->colorCount) CU(s, cudaMemset(s->colorCount, 0, 32 * sizeof(uint32_t)));
 	s->flowEpoch = 0;
-	CU(s, cudaMalloc(&s->rowColor, (size_t)allocRows * 3 * sizeof(uint32_t)));
+	CU(s, cudaMalloc(&s->rowColor, (size_t)allocRows * 3 * 2 * sizeof(uint32_t))); // light counts, then heavy counts
 	return SPH_OK;
 }
 
@@ -902,9 +915,11 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 		delete s;
 		return fail(nullptr, SPH_ERR_INVALID, "unknown solver %d", cfg->solver);
 	}
-	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 512u;
+	s->sweepCap = cfg->sweep_capacity ? cfg->sweep_capacity : 256u;
 	s->sweepAdaptive = cfg->sweep_capacity == 0;
 	s->useGraphs = !(cfg->flags & SPH_FLAG_NO_GRAPHS);
+	if (const char *e = getenv("SPHB200_HEAVY_FACTOR")) s->heavyFactor = std::max(1.0f, (float)atof(e)); // tuning knobs of the light / heavy split
+	if (const char *e = getenv("SPHB200_TEAM_DIV")) s->teamDiv = (uint32_t)std::max(2, atoi(e));
 	{
 		// the viscosity sweep stages positions + velocities + a 16-bit queue: 18 bytes per candidate and warp
 		int smemOptin = 0, sms = 0;
@@ -912,7 +927,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
 		if (sms > 0) s->numSMs = sms;
 		s->maxDynSmem = (size_t)std::min(std::max(smemOptin - 2048, 48 * 1024), 200 * 1024);
-		const uint32_t most = (uint32_t)(s->maxDynSmem / (SPH_SWEEP_WARPS * 18u)) / 32u * 32u;
+		const uint32_t most = (uint32_t)(s->maxDynSmem / (SPH_FLOW_WARPS * 18u)) / 32u * 32u;
 		if (s->sweepCap < 32 || s->sweepCap > most) {
 			delete s;
 			return fail(nullptr, SPH_ERR_INVALID, "sweep_capacity %u outside 32..%u (shared memory of device %d)", cfg->sweep_capacity, most, cfg->device);
@@ -967,8 +982,8 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	CUC(cudaMalloc(&s->cellNew, cap * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->rank, cap * sizeof(uint32_t)));
 	CUC(cudaMalloc(&s->slotId, cap * sizeof(uint32_t)));
-	CUC(cudaMalloc(&s->colorCount, 16 * sizeof(uint32_t)));
-	CUC(cudaMemset(s->colorCount, 0, 16 * sizeof(uint32_t)));
+	CUC(cudaMalloc(&s->colorCount, 32 * sizeof(uint32_t)));
+	CUC(cudaMemset(s->colorCount, 0, 32 * sizeof(uint32_t)));
 	s->strip.rank = cfg->rank;
 	s->strip.world = cfg->world_size;
 	s->strip.halo = cfg->halo_rows > 0 ? cfg->halo_rows : kDefaultHaloRows;
@@ -1170,7 +1185,7 @@ int sph_clear_particles(SphHandle s) {
 	s->steppedOnce = false;
 	set_counts_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, 0, 0);
 	CU(s, cudaMemsetAsync(s->cellStart, 0, ((size_t)s->grid.nCells + 1) * sizeof(uint32_t), s->stream));
-	CU(s, cudaMemsetAsync(s->colorCount, 0, 9 * sizeof(uint32_t), s->stream)); // no occupied cells: the sweeps have nothing to visit
+	CU(s, cudaMemsetAsync(s->colorCount, 0, 18 * sizeof(uint32_t), s->stream)); // no occupied cells: the sweeps have nothing to visit
 	CU(s, cudaGetLastError());
 	return SPH_OK;
 }
@@ -1490,12 +1505,27 @@ int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
 	}
 	rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
-	if (s->sweepAdaptive && s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
-		// shared-memory staging sized to twice the longest candidate list seen recently: a host that
-		// enqueues hundreds of steps ahead of the device (graph replay costs ~7 us per step) only sees
-		// old counts, and blocks that outgrow the staging fall back to the much slower L2 path
-		const uint32_t longest = s->hCtrLag->maxNbr;
-		if (longest) s->sweepCap = std::min(1024u, std::max(192u, ((2u * longest + 31u) / 32u) * 32u));
+	if (s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
+		// Per-warp staging capacity and heavy-cell threshold from the candidates per particle of a recent step (the
+		// host enqueues steps ahead of the device and only sees old counts): the capacity holds 2.2 x the AVERAGE list -
+		// the cells beyond it are the heavy ones, swept by whole blocks - in coarse steps and with hysteresis, because
+		// every new capacity is a new step graph.  A cell is also heavy from 6 x the average work m x T (m ~ T / 9).
+		const Counters &lag = *s->hCtrLag;
+		const float avg = lag.nOut ? (float)((double)lag.pairCandidates / (double)lag.nOut) : 0.0f;
+		if (avg > 0.0f && (s->capAvg == 0.0f || avg > 1.25f * s->capAvg || avg < 0.75f * s->capAvg)) {
+			s->capAvg = avg;
+			if (s->sweepAdaptive) {
+				static const uint32_t steps[] = { 256, 384, 512, 768, 1024 };
+				uint32_t cap = 1024;
+				for (uint32_t c : steps)
+					if ((float)c >= 2.2f * avg) {
+						cap = c;
+						break;
+					}
+				s->sweepCap = cap;
+			}
+			s->workHeavy = (uint32_t)std::min(4.0e9f, std::max(2048.0f, s->heavyFactor * avg * avg / 9.0f));
+		}
 		s->lagPending = false;
 	}
 	c.dt = dt;
@@ -1525,6 +1555,8 @@ int step_run(SphSim *s, const StepCtx &c, int parts) {
 	memset(&key, 0, sizeof(key));
 	key.parity = buffer_parity(s);
 	key.sweepCap = s->sweepCap;
+	key.gridSweepCap = s->gridSweepCap; // the viscosity sweep runs on the previous grid's lists
+	key.workHeavy = s->workHeavy;
 	key.nb = c.nb;
 	key.nbodies = (uint32_t)s->bodies.size();
 	key.haloMsgRecords = s->haloMsgRecords;
@@ -1571,6 +1603,7 @@ int step_run(SphSim *s, const StepCtx &c, int parts) {
 		g = &s->graphs.back();
 	}
 	CU(s, cudaGraphLaunch(g->exec, s->stream));
+	if (parts & GRID_BACK) s->gridSweepCap = s->sweepCap; // what the captured grid build classified its lists for
 	set_buffer_parity(s, g->parityAfter);
 	s->flowEpoch = g->flowEpochAfter;
 	s->exchanges += g->exchanges;
@@ -1582,7 +1615,7 @@ int step_finish(SphSim *s) {
 	CU(s, cudaGetLastError());
 	s->steps++;
 	s->steppedOnce = true;
-	if (s->sweepAdaptive && !s->lagPending) {
+	if (!s->lagPending) {
 		CU(s, cudaMemcpyAsync(s->hCtrLag, s->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, s->stream));
 		CU(s, cudaEventRecord(s->lagEvent, s->stream));
 		s->lagPending = true;
