@@ -207,8 +207,11 @@ def run_ours(args):
             sim.Update(DT)
         flush.fill_(1)
         barrier()
+        # clocks are sampled on rank 0 only (its numbers are the ones reported): eight processes polling NVML inside
+        # a 15 ms timed region contend for the driver and cost every rank ~6 % (profiles/bench_r2)
+        sample_clocks = not args.no_clock_sampler and rank == 0
         sampler = ClockSampler(local_rank)
-        if not args.no_clock_sampler:
+        if sample_clocks:
             sampler.start()
         sim.mark(0)
         for _ in range(steps):
@@ -216,7 +219,7 @@ def run_ours(args):
         sim.mark(1)
         ms = sim.elapsed_ms(0, 1)
         barrier()
-        clocks = sampler.stop() if not args.no_clock_sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler disabled"]}
+        clocks = sampler.stop() if sample_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler disabled" if rank == 0 else "sampled on rank 0"]}
         ms = all_max(ms)
         stats = sim.GetStats()  # raises if a capacity / lost / timeout flag was set on the device
         out = {"nx": nx, "n_total": n_total, "n_local": n_local, "cells": gx * gy, "grid": (gx, gy), "gravity": gravity, "ms": ms, "steps": steps,

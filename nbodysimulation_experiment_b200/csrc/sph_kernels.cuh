@@ -789,34 +789,35 @@ enum { SWEEP_DELTA = 0, SWEEP_VISCOSITY = 1 };
 // positions), so the range test of sph.h:488 is not repeated.
 template <class M, bool CHECK = true>
 __device__ __forceinline__ float2 sweep_delta_term(const PairParams &k, float2 xi, float2 ppi, float2 xj, bool &hit) {
-	// SPHComputeDelta, sph.h:483-495, then * 0.5f (demo4.cpp:250-251)
-	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-	float r2 = M::dot2(rx, rx, ry, ry);
+	// SPHComputeDelta, sph.h:483-495, then * 0.5f (demo4.cpp:250-251); (x, y) pairs as packed operations (sph_math.cuh)
+	const float2 rel = M::sub2(xj, xi);
+	float r2 = M::norm2(rel);
 	hit = CHECK ? (r2 < k.h2) : true;
 	if (!hit) return make_float2(0.0f, 0.0f);
 	float r, inv;
 	M::len_inv(r2, r, inv);
 	float t = M::sub(1.0f, M::mul(r, k.invH));
 	float d = M::mul(k.dt2, M::add(M::mul(ppi.x, t), M::mul(ppi.y, M::mul(t, t))));
-	return make_float2(M::mul(M::mul(d, M::mul(rx, inv)), 0.5f), M::mul(M::mul(d, M::mul(ry, inv)), 0.5f));
+	return M::scale2(M::scale2(M::scale2(rel, inv), d), 0.5f); // (d * (rel * inv)) * 0.5
 }
 
 template <class M, bool CHECK = true>
 __device__ __forceinline__ float2 sweep_viscosity_term(const PairParams &k, float2 xi, float2 vi, float2 xj, float2 vj, bool &hit) {
 	// SPHComputeViscosityForce, sph.h:497-512, then * 0.5f * deltaTime (demo4.cpp:233-234)
 	hit = false;
-	float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-	float r2 = M::dot2(rx, rx, ry, ry);
+	const float2 rel = M::sub2(xj, xi);
+	float r2 = M::norm2(rel);
 	if (CHECK && !(r2 < k.h2)) return make_float2(0.0f, 0.0f);
 	float r, inv;
 	M::len_inv(r2, r, inv);
 	float q = M::mul(r, k.invH);
-	float nx = M::mul(rx, inv), ny = M::mul(ry, inv);
-	float u = M::dot2(M::sub(vi.x, vj.x), nx, M::sub(vi.y, vj.y), ny);
+	const float2 n = M::scale2(rel, inv);
+	const float2 proj = M::mul2(M::sub2(vi, vj), n);
+	float u = M::add(proj.x, proj.y); // (vi - vj) . n: two products, one sum
 	if (!(u > 0.0f)) return make_float2(0.0f, 0.0f);
 	hit = true;
 	float f = M::mul(M::sub(1.0f, q), M::add(M::mul(k.sigma, u), M::mul(k.beta, M::mul(u, u))));
-	return make_float2(M::mul(M::mul(M::mul(f, nx), 0.5f), k.dt), M::mul(M::mul(M::mul(f, ny), 0.5f), k.dt));
+	return M::scale2(M::scale2(M::scale2(n, f), 0.5f), k.dt); // ((f * n) * 0.5) * dt
 }
 
 __device__ __forceinline__ float butterfly_sum(float v) {
@@ -936,15 +937,14 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 				float2 xj;
 				if (STAGED) xj = sPos[t];
 				else xj = (t < b.T) ? __ldcg(&pos[b.gidx(t)]) : make_float2(3.0e18f, 3.0e18f);
-				const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-				const bool hit = M::dot2(rx, rx, ry, ry) < k.h2;
+				const bool hit = M::norm2(M::sub2(xj, xi)) < k.h2;
 				const uint32_t mask = __ballot_sync(0xffffffffu, hit);
 				if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
 				nHit += (uint32_t)__popc(mask);
 			}
 			__syncwarp();
 			// stage 2: the pair terms, partner updated at once (demo4.cpp:233-234, 250-251)
-			float ax = 0.0f, ay = 0.0f;
+			float2 acc = make_float2(0.0f, 0.0f);
 			for (uint32_t q = lane; q < nHit; q += 32) {
 				const uint32_t t = queue[q];
 				bool hit;
@@ -952,11 +952,10 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 					float2 *slot = STAGED ? &sPos[t] : &pos[b.gidx(t)];
 					const float2 xj = STAGED ? *slot : __ldcg(slot);
 					const float2 hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit); // queued = within h, nothing moved it since stage 1
-					const float2 moved = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+					const float2 moved = Exact::add2(hlf, xj);
 					if (STAGED) *slot = moved;
 					else __stcg(slot, moved);
-					ax = __fsub_rn(ax, hlf.x);
-					ay = __fsub_rn(ay, hlf.y);
+					acc = Exact::sub2(acc, hlf);
 				} else {
 					const uint32_t j = STAGED ? 0u : b.gidx(t);
 					float2 *slot = STAGED ? &sVel[t] : &vel[j];
@@ -964,17 +963,15 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 					const float2 xj = STAGED ? sPos[t] : __ldcg(&pos[j]);
 					const float2 hlf = sweep_viscosity_term<M, false>(k, xi, vi, xj, vj, hit);
 					if (hit) {
-						const float2 moved = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+						const float2 moved = Exact::add2(hlf, vj);
 						if (STAGED) *slot = moved;
 						else __stcg(slot, moved);
-						ax = __fsub_rn(ax, hlf.x);
-						ay = __fsub_rn(ay, hlf.y);
+						acc = Exact::sub2(acc, hlf);
 					}
 				}
 			}
-			const float2 own = butterfly_sum2_lane0(ax, ay, lane);
-			ax = own.x;
-			ay = own.y;
+			const float2 own = butterfly_sum2_lane0(acc.x, acc.y, lane);
+			float ax = own.x, ay = own.y;
 			__syncwarp();
 			if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
 				if (STAGED) {
@@ -1123,8 +1120,7 @@ __device__ __forceinline__ void sweep_cell_team(const PairParams &k, const Sweep
 			// stage 1a: every warp tests its share of the 32-candidate trips
 			for (uint32_t tr = w; tr < nTrips; tr += SPH_TEAM_WARPS) {
 				const float2 xj = sPos[tr * 32u + lane];
-				const float rx = M::sub(xj.x, xi.x), ry = M::sub(xj.y, xi.y);
-				const uint32_t mask = __ballot_sync(0xffffffffu, M::dot2(rx, rx, ry, ry) < k.h2);
+				const uint32_t mask = __ballot_sync(0xffffffffu, M::norm2(M::sub2(xj, xi)) < k.h2);
 				if (lane == 0) tripMask[tr] = mask;
 			}
 			__syncthreads();
@@ -1157,11 +1153,11 @@ __device__ __forceinline__ void sweep_cell_team(const PairParams &k, const Sweep
 				if (PASS == SWEEP_DELTA) {
 					const float2 xj = sPos[t];
 					hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit);
-					sPos[t] = make_float2(__fadd_rn(hlf.x, xj.x), __fadd_rn(hlf.y, xj.y));
+					sPos[t] = Exact::add2(hlf, xj);
 				} else {
 					const float2 vj = sVel[t];
 					hlf = sweep_viscosity_term<M, false>(k, xi, vi, sPos[t], vj, hit);
-					if (hit) sVel[t] = make_float2(__fadd_rn(hlf.x, vj.x), __fadd_rn(hlf.y, vj.y));
+					if (hit) sVel[t] = Exact::add2(hlf, vj);
 					else hlf = make_float2(0.0f, 0.0f); // x - (+0) == x bit for bit
 				}
 				sTerm[q] = hlf;

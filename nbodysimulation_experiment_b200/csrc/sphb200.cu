@@ -1490,6 +1490,22 @@ struct StepCtx {
 	bool graphable;
 };
 
+// staging capacity and heavy-cell threshold for `avg` candidates per particle (step_prepare)
+void set_sweep_class(SphSim *s, float avg) {
+	s->capAvg = avg;
+	if (s->sweepAdaptive) {
+		static const uint32_t steps[] = { 256, 384, 512, 768, 1024 };
+		uint32_t cap = 1024;
+		for (uint32_t c : steps)
+			if ((float)c >= 2.2f * avg) {
+				cap = c;
+				break;
+			}
+		s->sweepCap = cap;
+	}
+	s->workHeavy = (uint32_t)std::min(4.0e9f, std::max(2048.0f, s->heavyFactor * avg * avg / 9.0f));
+}
+
 // host work ahead of a step's launches: emitters (demo4.cpp:296-299), body upload, staging capacity, strip bookkeeping
 int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
 	if (!(dt > 0.0f)) return fail(s, SPH_ERR_INVALID, "dt must be > 0");
@@ -1505,6 +1521,13 @@ int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
 	}
 	rc = upload_bodies(s);
 	if (rc != SPH_OK) return rc;
+	if (s->capAvg == 0.0f && s->params.particle_spacing > 0.0f) {
+		// before anything was measured: the scene's nominal density, 3x3 cells of (cell / spacing)^2 particles each -
+		// what a volume filled at particle_spacing (AddVolume, demo4.cpp:169-181) gives; a decision that changes
+		// only steps later costs a new step graph in the middle of somebody's timed region
+		const float perCell = s->grid.cell / s->params.particle_spacing;
+		set_sweep_class(s, 9.0f * perCell * perCell);
+	}
 	if (s->lagPending && cudaEventQuery(s->lagEvent) == cudaSuccess) {
 		// Per-warp staging capacity and heavy-cell threshold from the candidates per particle of a recent step (the
 		// host enqueues steps ahead of the device and only sees old counts): the capacity holds 2.2 x the AVERAGE list -
@@ -1512,20 +1535,7 @@ int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
 		// every new capacity is a new step graph.  A cell is also heavy from 6 x the average work m x T (m ~ T / 9).
 		const Counters &lag = *s->hCtrLag;
 		const float avg = lag.nOut ? (float)((double)lag.pairCandidates / (double)lag.nOut) : 0.0f;
-		if (avg > 0.0f && (s->capAvg == 0.0f || avg > 1.25f * s->capAvg || avg < 0.75f * s->capAvg)) {
-			s->capAvg = avg;
-			if (s->sweepAdaptive) {
-				static const uint32_t steps[] = { 256, 384, 512, 768, 1024 };
-				uint32_t cap = 1024;
-				for (uint32_t c : steps)
-					if ((float)c >= 2.2f * avg) {
-						cap = c;
-						break;
-					}
-				s->sweepCap = cap;
-			}
-			s->workHeavy = (uint32_t)std::min(4.0e9f, std::max(2048.0f, s->heavyFactor * avg * avg / 9.0f));
-		}
+		if (avg > 0.0f && (s->capAvg == 0.0f || avg > 1.3f * s->capAvg || avg < 0.7f * s->capAvg)) set_sweep_class(s, avg);
 		s->lagPending = false;
 	}
 	c.dt = dt;

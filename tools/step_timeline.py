@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--gravity", type=float, default=-10.0)
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-sync", action="store_true", help="enqueue all steps without waiting (as bench.py does); per-step times from events recorded between the steps")
     a = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     import torch
@@ -54,13 +55,25 @@ def main():
     if world > 1:
         dist.barrier()
     ms, host_ms = [], []
-    for _ in range(a.steps):
-        h0 = time.perf_counter()
-        sim.mark(0)
-        sim.Update(dt)
-        sim.mark(1)
-        ms.append(sim.elapsed_ms(0, 1))  # waits for the step
-        host_ms.append((time.perf_counter() - h0) * 1e3)
+    if a.no_sync:
+        stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+        evs[0].record(stream)
+        for k in range(a.steps):
+            h0 = time.perf_counter()
+            sim.Update(dt)
+            evs[k + 1].record(stream)
+            host_ms.append((time.perf_counter() - h0) * 1e3)
+        sim.Sync()
+        ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(a.steps)]
+    else:
+        for _ in range(a.steps):
+            h0 = time.perf_counter()
+            sim.mark(0)
+            sim.Update(dt)
+            sim.mark(1)
+            ms.append(sim.elapsed_ms(0, 1))  # waits for the step
+            host_ms.append((time.perf_counter() - h0) * 1e3)
     sim.GetStats()
     sim.close()
     mine = {"rank": rank, "device_ms": [round(x, 4) for x in ms], "host_ms": [round(x, 4) for x in host_ms], "setup_s": round(setup_s, 3)}
