@@ -52,9 +52,9 @@ BYTES_PER_PARTICLE_STEP = 176  # SURVEY.md 8(d) / BASELINE.md 4
 BYTES_PER_CELL_STEP = 16
 # algorithmic HBM bytes per particle of each phase (DESIGN.md "kernels")
 PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "reorder": 44, "density": 16, "delta": 24, "collide_velocity": 32}
-# integrate, viscosity sweep (1 launch, or 9 with --sweep warp/team), predict_key, scan (tiles, sums, add), colour lists (count, scan, fill),
+# integrate, viscosity sweep (1 launch, or 9 with --sweep warp/team), predict_key, scan (tile sums, apply), colour lists (count, fill),
 # scatter_ids, reorder, density, delta sweep (1 or 9), collide_velocity
-KERNELS_PER_STEP = {"gs": 14, "gs9": 30, "gather": 11}
+KERNELS_PER_STEP = {"gs": 12, "gs9": 28, "gather": 10}
 TRAFFIC_FILE = "r1_final_traffic.json"  # ncu --set full figures of the dominant kernel on the default workload
 
 

@@ -469,48 +469,87 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 	return before + inc - v;
 }
 
-__global__ void __launch_bounds__(SPH_THREADS) scan_tiles_kernel(const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ cellStart,
-                                                                uint32_t *__restrict__ tileSums, uint32_t nCells) {
+// 16 consecutive cells of one thread as four 16-byte accesses (the cell arrays are 256-byte aligned and a tile starts at
+// a multiple of 4096 cells); cells past the end read as empty
+__device__ __forceinline__ void load_cells16(const uint32_t *__restrict__ src, uint32_t first, uint32_t nCells, uint32_t v[SPH_SCAN_ITEMS]) {
+	if (first + SPH_SCAN_ITEMS <= nCells) {
+#pragma unroll
+		for (int q = 0; q < SPH_SCAN_ITEMS / 4; ++q) {
+			const uint4 x = *reinterpret_cast<const uint4 *>(src + first + 4 * q);
+			v[4 * q] = x.x;
+			v[4 * q + 1] = x.y;
+			v[4 * q + 2] = x.z;
+			v[4 * q + 3] = x.w;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SPH_SCAN_ITEMS; ++k) v[k] = (first + k < nCells) ? src[first + k] : 0u;
+	}
+}
+
+// Two launches (was three, one of them a single block): the tiles' sums, then every tile adds up the sums of the tiles
+// before it by itself (at most a few thousand words, 256 threads) and scans its cells behind that offset.
+__global__ void __launch_bounds__(SPH_THREADS) scan_tile_sums_kernel(const uint32_t *__restrict__ cellCount, uint32_t *__restrict__ tileSums, uint32_t nCells) {
+	uint32_t v[SPH_SCAN_ITEMS], sum = 0;
+	load_cells16(cellCount, blockIdx.x * SPH_SCAN_TILE + threadIdx.x * SPH_SCAN_ITEMS, nCells, v);
+#pragma unroll
+	for (int k = 0; k < SPH_SCAN_ITEMS; ++k) sum += v[k];
+	__shared__ uint32_t warpSums[SPH_THREADS / 32];
+	sum = warp_sum(sum);
+	if (lane_id() == 0) warpSums[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t total = 0;
+#pragma unroll
+		for (int w = 0; w < SPH_THREADS / 32; ++w) total += warpSums[w];
+		tileSums[blockIdx.x] = total;
+	}
+}
+
+__global__ void __launch_bounds__(SPH_THREADS) scan_apply_kernel(const uint32_t *__restrict__ cellCount, const uint32_t *__restrict__ tileSums,
+                                                                uint32_t *__restrict__ cellStart, uint32_t nCells, Counters *__restrict__ ctr) {
+	// sum of the tiles before this one
+	__shared__ uint32_t warpPart[SPH_THREADS / 32];
+	uint32_t before = 0;
+	for (uint32_t j = threadIdx.x; j < blockIdx.x; j += SPH_THREADS) before += tileSums[j];
+	before = warp_sum(before);
+	if (lane_id() == 0) warpPart[threadIdx.x >> 5] = before;
 	const uint32_t first = blockIdx.x * SPH_SCAN_TILE + threadIdx.x * SPH_SCAN_ITEMS;
 	uint32_t v[SPH_SCAN_ITEMS], sum = 0;
+	load_cells16(cellCount, first, nCells, v);
 #pragma unroll
-	for (int k = 0; k < SPH_SCAN_ITEMS; ++k) {
-		v[k] = (first + k < nCells) ? cellCount[first + k] : 0u;
-		sum += v[k];
-	}
+	for (int k = 0; k < SPH_SCAN_ITEMS; ++k) sum += v[k];
+	__syncthreads();
+	uint32_t offset = 0;
+#pragma unroll
+	for (int w = 0; w < SPH_THREADS / 32; ++w) offset += warpPart[w];
 	uint32_t total;
-	uint32_t run = block_exclusive_scan(sum, &total);
+	uint32_t run = offset + block_exclusive_scan(sum, &total);
+	if (first + SPH_SCAN_ITEMS <= nCells) {
 #pragma unroll
-	for (int k = 0; k < SPH_SCAN_ITEMS; ++k) {
-		if (first + k < nCells) cellStart[first + k] = run;
-		run += v[k];
+		for (int q = 0; q < SPH_SCAN_ITEMS / 4; ++q) {
+			uint4 x;
+			x.x = run;
+			run += v[4 * q];
+			x.y = run;
+			run += v[4 * q + 1];
+			x.z = run;
+			run += v[4 * q + 2];
+			x.w = run;
+			run += v[4 * q + 3];
+			*reinterpret_cast<uint4 *>(cellStart + first + 4 * q) = x;
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SPH_SCAN_ITEMS; ++k) {
+			if (first + k < nCells) cellStart[first + k] = run;
+			run += v[k];
+		}
 	}
-	if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of the tile sums in place, total -> cellStart[nCells] and ctr->nOut
-__global__ void __launch_bounds__(SPH_THREADS) scan_sums_kernel(uint32_t *__restrict__ tileSums, uint32_t nTiles, uint32_t *__restrict__ cellStart,
-                                                               uint32_t nCells, Counters *__restrict__ ctr) {
-	uint32_t carry = 0;
-	for (uint32_t base = 0; base < nTiles; base += SPH_THREADS) {
-		const uint32_t idx = base + threadIdx.x;
-		const uint32_t v = idx < nTiles ? tileSums[idx] : 0u;
-		uint32_t total;
-		const uint32_t ex = block_exclusive_scan(v, &total);
-		if (idx < nTiles) tileSums[idx] = carry + ex;
-		carry += total;
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { // the last tile knows the total
+		cellStart[nCells] = offset + total;
+		ctr->nOut = offset + total;
 	}
-	if (threadIdx.x == 0) {
-		cellStart[nCells] = carry;
-		ctr->nOut = carry;
-	}
-}
-
-__global__ void __launch_bounds__(SPH_THREADS) scan_add_kernel(uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ tileSums, uint32_t nCells) {
-	const uint32_t off = tileSums[blockIdx.x];
-	const uint32_t first = blockIdx.x * SPH_SCAN_TILE;
-	for (uint32_t k = threadIdx.x; k < SPH_SCAN_TILE; k += SPH_THREADS)
-		if (first + k < nCells) cellStart[first + k] += off;
 }
 
 // ---- colour lists in row-major order ---------------------------------------------------------------
@@ -544,9 +583,11 @@ struct SweepClass {
 #define SPH_FLOW_FLAGS 4u
 __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kernel(GridDesc g, SweepClass cls, uint32_t *__restrict__ cellCount,
                                                                                 const uint32_t *__restrict__ cellStart, uint32_t *__restrict__ rowColor,
-                                                                                uint32_t *__restrict__ flow) {
+                                                                                uint32_t *__restrict__ colorCount, uint32_t *__restrict__ flow) {
 	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
+	if (blockIdx.x == 0 && threadIdx.x < 18) colorCount[threadIdx.x] = 0u; // color_rows_fill_kernel writes the totals of the colours that have rows
+	if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 36) flow[threadIdx.x - 32] = 0u; // ticket counters (light, heavy) of the next two passes over this grid
 	if (wid >= nRows * 3u) return;
 	const uint32_t row = wid / 3u, a = wid - row * 3u;
 	uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
@@ -585,42 +626,9 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_count_kerne
 	}
 }
 
-// eighteen warps, one per (class, colour k = (row mod 3)*3 + a): exclusive scan of rowColor over that colour's rows, in place
-__global__ void __launch_bounds__(18 * 32) color_rows_scan_kernel(GridDesc g, uint32_t *__restrict__ rowColor, uint32_t *__restrict__ colorCount,
-                                                                  uint32_t *__restrict__ flow) {
-	const uint32_t kk = threadIdx.x >> 5, lane = lane_id();
-	if (threadIdx.x < 4) flow[threadIdx.x] = 0u; // ticket counters (light, heavy) of the next two passes over this grid
-	const uint32_t cls = kk / 9u, k = kk - cls * 9u;
-	const uint32_t b = k / 3u, a = k - b * 3u;
-	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
-	uint32_t *rc = rowColor + (size_t)cls * nRows * 3u;
-	const uint32_t r0 = (b + 3u - (uint32_t)g.rowLo % 3u) % 3u; // first local row whose global row is b mod 3
-	uint32_t running = 0;
-	for (uint32_t base = r0; base < nRows; base += 4u * 96u) { // four loads in flight per round trip
-		uint32_t v[4];
-#pragma unroll
-		for (int u = 0; u < 4; ++u) {
-			const uint32_t row = base + 96u * (uint32_t)u + 3u * lane;
-			v[u] = row < nRows ? rc[row * 3u + a] : 0u;
-		}
-#pragma unroll
-		for (int u = 0; u < 4; ++u) {
-			const uint32_t row = base + 96u * (uint32_t)u + 3u * lane;
-			uint32_t inc = v[u];
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-				if ((int)lane >= o) inc += up;
-			}
-			if (row < nRows) rc[row * 3u + a] = running + inc - v[u];
-			running += __shfl_sync(0xffffffffu, inc, 31);
-		}
-	}
-	if (lane == 0) colorCount[kk] = running;
-}
-
 __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel(GridDesc g, const uint32_t *__restrict__ cellCount, const uint32_t *__restrict__ rowColor,
-                                                                               uint32_t *__restrict__ colorList, uint32_t listStride) {
+                                                                               uint32_t *__restrict__ colorList, uint32_t listStride,
+                                                                               uint32_t *__restrict__ colorCount) {
 	const uint32_t wid = blockIdx.x * SPH_ROWLIST_WARPS + (threadIdx.x >> 5), lane = lane_id();
 	const uint32_t nRows = (uint32_t)(g.rowHi - g.rowLo);
 	if (wid >= nRows * 3u) return;
@@ -628,7 +636,20 @@ __global__ void __launch_bounds__(SPH_ROWLIST_WARPS * 32) color_rows_fill_kernel
 	const uint32_t k = ((row + (uint32_t)g.rowLo) % 3u) * 3u + a;
 	const uint32_t *cc = cellCount + (size_t)row * (uint32_t)g.gx;
 	uint32_t *list = colorList + (size_t)k * listStride;
-	uint32_t at = rowColor[wid], atHeavy = rowColor[nRows * 3u + wid];
+	// Where this row's cells start in its colour's lists: the counts of the rows of the same colour below it (rows
+	// row-3, row-6, ...), summed by the warp itself - a few hundred words instead of a single-block scan launch.  The
+	// colour's topmost row also knows the totals.
+	uint32_t at = 0, atHeavy = 0;
+	for (int r = (int)row - 3 * (int)(lane + 1u); r >= 0; r -= 96) {
+		at += rowColor[(uint32_t)r * 3u + a];
+		atHeavy += rowColor[nRows * 3u + (uint32_t)r * 3u + a];
+	}
+	at = warp_sum(at);
+	atHeavy = warp_sum(atHeavy);
+	if (row + 3u >= nRows && lane == 0) {
+		colorCount[k] = at + rowColor[wid];
+		colorCount[9u + k] = atHeavy + rowColor[nRows * 3u + wid];
+	}
 	for (uint32_t c0 = a; c0 < (uint32_t)g.gx; c0 += 4u * 96u) { // warp-uniform trip count, four loads in flight per round trip
 		uint32_t v[4];
 #pragma unroll

@@ -151,6 +151,7 @@ struct SphSim {
 	uint32_t workHeavy = 6000;       // m x T from which a cell is swept by a whole block (SweepClass)
 	float heavyFactor = 6.0f;        // ... as a multiple of the average m x T
 	uint32_t teamDiv = 2;            // at most 1/teamDiv of the sweep's blocks work as teams
+	float capFactor = 2.2f;          // per-warp staging capacity as a multiple of the average candidate list
 	float capAvg = 0.0f;             // candidates per particle the adaptive capacity was last chosen for
 	bool sweepAdaptive = true;       // pick the staging capacity from the candidates per particle of recent steps
 	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
@@ -527,18 +528,16 @@ int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool time
 		if (rc != SPH_OK) return rc;
 	}
 	if (timed) record_phase(s, PH_EXCHANGE + 1);
-	scan_tiles_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->cellStart, s->tileSums, g.nCells);
-	scan_sums_kernel<<<1, SPH_THREADS, 0, s->stream>>>(s->tileSums, s->nTiles, s->cellStart, g.nCells, s->dCtr);
-	scan_add_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellStart, s->tileSums, g.nCells);
+	scan_tile_sums_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->tileSums, g.nCells);
+	scan_apply_kernel<<<s->nTiles, SPH_THREADS, 0, s->stream>>>(s->cellCount, s->tileSums, s->cellStart, g.nCells, s->dCtr);
 	if (s->cfg.solver == SPH_SOLVER_COLORED_GS) { // occupied cells per colour, each list in row-major order
 		const unsigned rowWarps = (unsigned)(g.rowHi - g.rowLo) * 3u, rowBlocks = (rowWarps + SPH_ROWLIST_WARPS - 1) / SPH_ROWLIST_WARPS;
 		// light / heavy split of the lists (sph_kernels.cuh, "LIGHT and HEAVY cells"): by this grid's staging capacity
 		s->gridSweepCap = s->sweepCap;
 		const SweepClass cls = { s->sweepCap, s->workHeavy };
-		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, cls, s->cellCount, s->cellStart, s->rowColor, s->sweepFlow);
-		color_rows_scan_kernel<<<1, 18 * 32, 0, s->stream>>>(g, s->rowColor, s->colorCount, s->sweepFlow);
+		color_rows_count_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, cls, s->cellCount, s->cellStart, s->rowColor, s->colorCount, s->sweepFlow);
 		s->flowEpoch = 0; // the done flags are fresh: the next sweep over this grid is its first
-		color_rows_fill_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->colorList, s->listStride);
+		color_rows_fill_kernel<<<rowBlocks, SPH_ROWLIST_WARPS * 32, 0, s->stream>>>(g, s->cellCount, s->rowColor, s->colorList, s->listStride, s->colorCount);
 	}
 	if (timed) record_phase(s, PH_SCAN + 1);
 	scatter_ids_kernel<<<nb, SPH_THREADS, 0, s->stream>>>(g, s->dCtr, s->cellNew, s->rank, s->id.in(), s->cellStart, s->slotId);
@@ -920,6 +919,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	s->useGraphs = !(cfg->flags & SPH_FLAG_NO_GRAPHS);
 	if (const char *e = getenv("SPHB200_HEAVY_FACTOR")) s->heavyFactor = std::max(1.0f, (float)atof(e)); // tuning knobs of the light / heavy split
 	if (const char *e = getenv("SPHB200_TEAM_DIV")) s->teamDiv = (uint32_t)std::max(2, atoi(e));
+	if (const char *e = getenv("SPHB200_CAP_FACTOR")) s->capFactor = std::max(1.0f, (float)atof(e));
 	{
 		// the viscosity sweep stages positions + velocities + a 16-bit queue: 18 bytes per candidate and warp
 		int smemOptin = 0, sms = 0;
@@ -1497,7 +1497,7 @@ void set_sweep_class(SphSim *s, float avg) {
 		static const uint32_t steps[] = { 256, 384, 512, 768, 1024 };
 		uint32_t cap = 1024;
 		for (uint32_t c : steps)
-			if ((float)c >= 2.2f * avg) {
+			if ((float)c >= s->capFactor * avg) {
 				cap = c;
 				break;
 			}
