@@ -138,6 +138,9 @@ int sph_clear_particles(SphHandle h); /* ClearParticles */
 int sph_clear_emitters(SphHandle h);  /* ClearEmitters */
 /* AddParticle in bulk: n positions and initial accelerations ("force", consumed by the first
  * integrate, demo4.cpp:146,306-308); acc_xy may be NULL (zero).  Indices are creation order. */
+/* On a y-strip (world_size > 1) every rank is given the WHOLE list, in the same order, and keeps the particles whose
+ * cell row it owns; creation indices are the same on every rank.  sph_add_volume, the emitters (every rank runs the
+ * same emitter clocks and libc rand() sequence; sph_load_scenario seeds it) and sph_load_scenario go through here. */
 int sph_add_particles(SphHandle h, size_t n, const float *pos_xy, const float *acc_xy, uint64_t *first_index);
 /* AddVolume, demo4.cpp:169-181: row-major block with the libc rand() jitter of vecmath.h:317-322 */
 int sph_add_volume(SphHandle h, float cx, float cy, float fx, float fy, int count_x, int count_y, float spacing);
@@ -178,7 +181,9 @@ int sph_get_stats(SphHandle h, SphStats *out); /* GetStats */
  * pressure, nearPressure = 12 floats.  Record i is the i-th created particle, written at
  * dst + i*stride (stride >= 48).  With world_size > 1 only this rank's particles are written. */
 int sph_read_particles(SphHandle h, void *dst, size_t stride);
-int sph_write_particles(SphHandle h, const void *src, size_t stride); /* inject cur/prev/acc/vel (+ rho,P fields) and re-file the grid */
+/* inject cur/prev/acc/vel (+ rho,P fields) and re-file the grid; on a y-strip every rank is given the whole state
+ * (sph_particle_count rows, creation order) and keeps the rows of its window, ghost rows included */
+int sph_write_particles(SphHandle h, const void *src, size_t stride);
 /* Render()'s particle section, demo4.cpp:520-531: positions at pos_stride (>= 8) and the colours of
  * SPHGetParticleColor (sph.h:683-695) at color_stride (>= 16), both in creation order.  The state is
  * snapshotted on the device and copied on a second stream: with pinned buffers (sph_host_alloc) the

@@ -1616,6 +1616,36 @@ __global__ void __launch_bounds__(SPH_THREADS) volume_hashed_kernel(GridDesc g, 
 	}
 }
 
+// Strips: AddParticle in bulk (sph_add_particles, emitters) and state injection (sph_write_particles).  Every rank is
+// given the WHOLE list and keeps the particles whose cell row it owns; the creation index is the position in the list,
+// the same on every rank.  `rec` (optional) carries the full ParticleData rows of an injected state; an injected state is
+// kept for the whole local window [rowBegin, rowEnd) = owned + ghost rows, because the ghosts' velocities cannot be
+// rebuilt from what a neighbour exchange carries.
+__global__ void __launch_bounds__(SPH_THREADS) append_owned_kernel(GridDesc g, int rowBegin, int rowEnd, Counters *__restrict__ ctr, uint32_t capacity, uint32_t count,
+                                                                  const float2 *__restrict__ posIn, const float2 *__restrict__ accIn,
+                                                                  const ParticleRecord *__restrict__ rec, uint32_t firstId, float2 *__restrict__ pos,
+                                                                  float2 *__restrict__ prev, float2 *__restrict__ vel, float2 *__restrict__ acc,
+                                                                  float2 *__restrict__ dens, float2 *__restrict__ press, uint32_t *__restrict__ id) {
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+		const float2 p = rec ? rec[k].cur : posIn[k];
+		int cx, cy;
+		cell_of(g, p, cx, cy);
+		if (cy < rowBegin || cy >= rowEnd) continue;
+		const uint32_t slot = atomicAdd(&ctr->n, 1u);
+		if (slot >= capacity) {
+			atomicOr(&ctr->overflow, 1u);
+			continue;
+		}
+		pos[slot] = p;
+		prev[slot] = rec ? rec[k].prev : p; // ParticleData(pos), demo4.h:101-106
+		vel[slot] = rec ? rec[k].vel : make_float2(0.0f, 0.0f);
+		acc[slot] = rec ? rec[k].acc : (accIn ? accIn[k] : make_float2(0.0f, 0.0f));
+		dens[slot] = rec ? make_float2(rec[k].rho, rec[k].rhoNear) : make_float2(0.0f, 0.0f);
+		press[slot] = rec ? make_float2(rec[k].P, rec[k].PNear) : make_float2(0.0f, 0.0f);
+		id[slot] = firstId + k;
+	}
+}
+
 __global__ void clamp_count_kernel(Counters *ctr, uint32_t capacity) {
 	if (ctr->n > capacity) ctr->n = capacity;
 }

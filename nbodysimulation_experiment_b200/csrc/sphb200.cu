@@ -501,29 +501,34 @@ enum { GRID_FRONT = 1, GRID_EXCHANGE = 2, GRID_BACK = 4, GRID_ALL = 7 };
 // neighbours' records on.  The peer transport runs all of it as one graph; the NCCL transport enqueues its send/recv
 // (GRID_EXCHANGE, not capturable on this stack) between two graphs; strips of one process (sph_step_group) run every
 // strip's FRONT before any BACK, so that no kernel ever waits for work the host has not enqueued yet.
-int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed, int parts = GRID_ALL) {
+// exchange = false: a purely local re-filing (state injection on strips: every rank was given its whole window, ghost
+// rows included, so nothing is sent and nothing is awaited)
+int launch_grid_build(SphSim *s, float dt, bool doPredict, bool carry, bool timed, int parts = GRID_ALL, bool exchange = true) {
 	const GridDesc &g = s->grid;
 	const unsigned nb = blocks_for(s->hostN);
+	const bool strips = s->strip.world > 1 && exchange;
 	if (parts & GRID_FRONT) {
-		if (s->strip.world > 1 && s->transport == TR_NONE) return fail(s, SPH_ERR_STATE, "sph_comm_init / sph_comm_init_local was not called on this multi-GPU handle");
+		if (strips && s->transport == TR_NONE) return fail(s, SPH_ERR_STATE, "sph_comm_init / sph_comm_init_local was not called on this multi-GPU handle");
 		CU(s, cudaMemsetAsync(s->cellCount, 0, (size_t)g.nCells * sizeof(uint32_t), s->stream));
-		predict_key_kernel<<<blocks_for((s->hostN + 1) / 2), SPH_THREADS, 0, s->stream>>>(g, s->strip, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
+		StripDesc sd = s->strip;
+		if (!exchange) sd.world = 1; // keep what lies in the window, send nothing
+		predict_key_kernel<<<blocks_for((s->hostN + 1) / 2), SPH_THREADS, 0, s->stream>>>(g, sd, s->dCtr, s->pos.in(), s->prev.in(), s->vel.in(), s->id.in(), s->cellOf.in(), s->cellNew,
 		                                                      s->rank, s->cellCount, dt, doPredict ? 1 : 0);
 		// from the next grid on, authority follows the rows this grid is built for
 		s->strip.authLo = g.ownLo;
 		s->strip.authHi = g.ownHi;
 		if (timed) record_phase(s, PH_PREDICT + 1);
-		if (s->strip.world > 1) {
+		if (strips) {
 			int rc = exchange_front(s);
 			if (rc != SPH_OK) return rc;
 		}
 	}
-	if ((parts & GRID_EXCHANGE) && s->strip.world > 1 && s->transport == TR_NCCL) {
+	if ((parts & GRID_EXCHANGE) && strips && s->transport == TR_NCCL) {
 		int rc = exchange_nccl(s);
 		if (rc != SPH_OK) return rc;
 	}
 	if (!(parts & GRID_BACK)) return SPH_OK;
-	if (s->strip.world > 1) {
+	if (strips) {
 		int rc = exchange_back(s);
 		if (rc != SPH_OK) return rc;
 	}
@@ -857,6 +862,40 @@ int append_particles(SphSim *s, size_t n, const float *posXY, const float *accXY
 	// n grows, nSorted stays: the newcomers are in nobody's neighbour list yet (demo4.cpp:148)
 	grow_count_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, (uint32_t)s->hostN);
 	CU(s, cudaGetLastError());
+	return SPH_OK;
+}
+
+// Strips: the same list on every rank, each keeps what lands in its rows (append_owned_kernel).  `n` on the device
+// grows by what was kept; the host only knows the bound.
+int append_particles_owned(SphSim *s, size_t n, const float *posXY, const float *accXY, const void *records, size_t recStride, uint64_t *firstIndex) {
+	if (firstIndex) *firstIndex = s->nextId;
+	if (n == 0) return SPH_OK;
+	if (s->nextId + n > 0xFFFFFF00ull) return fail(s, SPH_ERR_CAPACITY, "particle ids exceed 32 bits");
+	float2 *dPos = nullptr, *dAcc = nullptr;
+	ParticleRecord *dRec = nullptr;
+	if (records) {
+		CU(s, cudaMalloc(&dRec, n * sizeof(ParticleRecord)));
+		CU(s, copy_strided(dRec, sizeof(ParticleRecord), records, recStride, sizeof(ParticleRecord), n, cudaMemcpyHostToDevice, s->stream));
+	} else {
+		CU(s, cudaMalloc(&dPos, n * sizeof(float2)));
+		CU(s, cudaMemcpyAsync(dPos, posXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+		if (accXY) {
+			CU(s, cudaMalloc(&dAcc, n * sizeof(float2)));
+			CU(s, cudaMemcpyAsync(dAcc, accXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+		}
+	}
+	const bool window = records != nullptr; // an injected state also fills the ghost rows (see append_owned_kernel)
+	append_owned_kernel<<<blocks_for(n), SPH_THREADS, 0, s->stream>>>(s->grid, window ? s->grid.rowLo : s->grid.ownLo, window ? s->grid.rowHi : s->grid.ownHi, s->dCtr,
+	                                                                s->capacity, (uint32_t)n, dPos, dAcc, dRec, (uint32_t)s->nextId, s->pos.in(),
+	                                                                s->prev.in(), s->vel.in(), s->acc.in(), s->dens.in(), s->press.in(), s->id.in());
+	clamp_count_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, s->capacity);
+	CU(s, cudaGetLastError());
+	CU(s, cudaStreamSynchronize(s->stream)); // the pageable sources and the staging buffers must outlive the copies
+	cudaFree(dPos);
+	cudaFree(dAcc);
+	cudaFree(dRec);
+	s->accFrom = 0u;
+	s->nextId += n;
 	return SPH_OK;
 }
 
@@ -1198,7 +1237,7 @@ int sph_clear_emitters(SphHandle s) {
 int sph_add_particles(SphHandle s, size_t n, const float *posXY, const float *accXY, uint64_t *firstIndex) {
 	ENTER(s);
 	if (n && !posXY) return fail(s, SPH_ERR_INVALID, "null positions");
-	if (s->cfg.world_size > 1) return fail(s, SPH_ERR_STATE, "host-side particle lists are single-GPU; use sph_add_volume_hashed with strips");
+	if (s->cfg.world_size > 1) return append_particles_owned(s, n, posXY, accXY, nullptr, 0, firstIndex); // every rank is given the whole list
 	int rc = append_particles(s, n, posXY, accXY, firstIndex);
 	if (rc != SPH_OK) return rc;
 	// the pageable source must stay valid until the copies ran
@@ -1294,13 +1333,14 @@ int sph_local_particle_count(SphHandle s, uint64_t *out) {
 }
 int sph_particle_count(SphHandle s, uint64_t *out) {
 	ENTER(s);
-	if (out) *out = s->hostN;
+	// strips: the particles of the whole simulation (every rank is told about every creation); what this rank holds is
+	// sph_local_particle_count
+	if (out) *out = s->cfg.world_size > 1 ? s->nextId : s->hostN;
 	return SPH_OK;
 }
 
 // UpdateEmitter, demo4.cpp:257-284 — clock and rand() on the host, particles appended on the device
-static int update_emitters(SphSim *s, float dt) {
-	std::vector<float> pos, acc;
+static void emit_particles(SphSim *s, float dt, std::vector<float> &pos, std::vector<float> &acc) {
 	const float spacing = s->params.particle_spacing;
 	const float invDt = 1.0f / dt;
 	const float h = s->params.kernel_height;
@@ -1334,6 +1374,10 @@ static int update_emitters(SphSim *s, float dt) {
 		}
 		if (e.totalElapsed >= e.duration) e.active = 0; // :280-282
 	}
+}
+static int update_emitters(SphSim *s, float dt) {
+	std::vector<float> pos, acc;
+	emit_particles(s, dt, pos, acc);
 	if (pos.empty()) return SPH_OK;
 	return sph_add_particles(s, pos.size() / 2, pos.data(), acc.data(), nullptr);
 }
@@ -1507,12 +1551,14 @@ void set_sweep_class(SphSim *s, float avg) {
 }
 
 // host work ahead of a step's launches: emitters (demo4.cpp:296-299), body upload, staging capacity, strip bookkeeping
-int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance) {
+int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance, bool emit = true) {
 	if (!(dt > 0.0f)) return fail(s, SPH_ERR_INVALID, "dt must be > 0");
 	if (s->cfg.world_size > 1 && s->transport == TR_NONE) return fail(s, SPH_ERR_STATE, "call sph_comm_init (or sph_comm_init_local) before stepping a multi-GPU handle");
-	if (s->cfg.world_size > 1 && !s->emitters.empty()) return fail(s, SPH_ERR_STATE, "emitters are single-GPU");
 	int rc;
-	if (!s->emitters.empty()) {
+	// (strips, one process per GPU: every rank runs the same emitter clocks and the same rand() sequence - seeded
+	// alike, sph_load_scenario - so all ranks emit the same list and each keeps what lands in its rows; strips of one
+	// process share ONE rand() stream: sph_step_group emits once, on the first strip, and hands the list to all)
+	if (!s->emitters.empty() && emit) {
 		const auto t0 = std::chrono::steady_clock::now();
 		rc = update_emitters(s, dt);
 		if (rc != SPH_OK) return rc;
@@ -1684,10 +1730,23 @@ int sph_step_group(SphHandle *handles, int32_t n, float dt) {
 		int rc = plan_rebalance_group(handles, n);
 		if (rc != SPH_OK) return rc;
 	}
+	// emitters: ONE rand() stream per process, so the first strip's emitters run (UpdateEmitter, demo4.cpp:257-284) and every
+	// strip is handed the list
+	if (!first->emitters.empty()) {
+		std::vector<float> pos, acc;
+		const auto t0 = std::chrono::steady_clock::now();
+		emit_particles(first, dt, pos, acc);
+		for (int r = 0; r < n && !pos.empty(); ++r) {
+			int rc = sph_add_particles(handles[r], pos.size() / 2, pos.data(), acc.data(), nullptr);
+			if (rc != SPH_OK) return rc;
+		}
+		first->hostEmitterMs += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		first->hostEmitterSteps++;
+	}
 	std::vector<StepCtx> ctx((size_t)n);
 	for (int r = 0; r < n; ++r) {
 		DeviceScope dev(handles[r]);
-		int rc = step_prepare(handles[r], dt, ctx[(size_t)r], false);
+		int rc = step_prepare(handles[r], dt, ctx[(size_t)r], false, false);
 		if (rc == SPH_OK) rc = step_run(handles[r], ctx[(size_t)r], GRID_FRONT);
 		if (rc != SPH_OK) return rc;
 	}
@@ -1831,7 +1890,24 @@ int sph_read_particles(SphHandle s, void *dst, size_t stride) {
 int sph_write_particles(SphHandle s, const void *src, size_t stride) {
 	ENTER(s);
 	if (!src || stride < sizeof(ParticleRecord)) return fail(s, SPH_ERR_INVALID, "stride must be >= 48");
-	if (s->cfg.world_size > 1) return fail(s, SPH_ERR_STATE, "state injection is single-GPU");
+	if (s->cfg.world_size > 1) {
+		// strips: every rank is given the whole state (nextId rows, creation order) and keeps its rows; the ghost copies
+		// arrive with the exchange of the re-filing pass below
+		const uint64_t total = s->nextId;
+		if (total == 0) return SPH_OK;
+		set_counts_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, 0, 0);
+		s->nextId = 0;
+		int rcw = append_particles_owned(s, (size_t)total, nullptr, nullptr, src, stride, nullptr);
+		if (rcw != SPH_OK) return rcw;
+		s->accFrom = 0;
+		begin_step_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
+		rcw = launch_grid_build(s, 1.0f, false, true, false, GRID_ALL, false); // local re-filing, no exchange
+		if (rcw != SPH_OK) return rcw;
+		commit_kernel<<<1, 1, 0, s->stream>>>(s->dCtr);
+		CU(s, cudaGetLastError());
+		CU(s, cudaStreamSynchronize(s->stream));
+		return SPH_OK;
+	}
 	if (s->hostN == 0) return SPH_OK;
 	if (!s->dRecords) CU(s, cudaMalloc(&s->dRecords, (size_t)s->capacity * sizeof(ParticleRecord)));
 	const uint32_t n = (uint32_t)s->hostN;

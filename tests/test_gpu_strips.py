@@ -129,3 +129,65 @@ def test_group_refuses_plain_step_and_wrong_order():
     with pytest.raises(SphError):
         StripGroup(sims)  # already wired
     group.close()
+
+
+# ---- the reference's own scenes on strips: host-side particle lists, emitters, state injection --------------------------
+def reference_scene_on_strips(scene, steps, world, halo_rows=0, inject=None):
+    """LoadScenario on every strip (the whole list goes to every rank, each keeps its rows), `steps` updates -> records
+    merged by creation id"""
+    from nbodysimulation_experiment_b200 import ParticleSimulation, StripGroup, strips
+
+    sims = [ParticleSimulation(rank=r, world_size=world, max_particles=20000, halo_capacity=20000, halo_rows=halo_rows) for r in range(world)]
+    for s in sims:
+        s.LoadScenario(scene, seed=1)
+        if inject is not None:
+            s.put_particles(inject)
+    group = StripGroup(sims)
+    for _ in range(steps):
+        group.Update(DT)
+    parts = []
+    for s in sims:
+        got = s.read_owned(records=True)
+        s.GetStats()
+        parts.append((got["ids"].copy(), got["records"].copy()))
+    total = sims[0].GetParticleCount()
+    merged = strips.merge_owned(parts, total)
+    group.close()
+    return merged
+
+
+def reference_scene_single(scene, steps, inject=None):
+    from nbodysimulation_experiment_b200 import ParticleSimulation
+
+    one = ParticleSimulation()
+    one.LoadScenario(scene, seed=1)
+    if inject is not None:
+        one.put_particles(inject)
+    for _ in range(steps):
+        one.Update(DT)
+    out = one.particles()
+    one.GetStats()
+    one.close()
+    return out
+
+
+@pytest.mark.parametrize("scene,steps,world,halo", [(0, 48, 2, 0), (3, 60, 2, 0), (5, 150, 2, 0), (7, 120, 2, 0), (4, 120, 3, 6)])
+def test_reference_scenes_on_strips_match_the_single_gpu_run_bitwise(scene, steps, world, halo):
+    """sph_add_volume / emitters (demo4.cpp:169-181, 257-284) on strips: volumes with the libc rand() jitter, emitters
+    that change N every few frames, boxes and a circle - the same bits as one GPU.  (18 grid rows: two strips of 9 rows
+    with the default 7-row halo, or three of 6 with a 6-row halo.)"""
+    ref = reference_scene_single(scene, steps)
+    multi = reference_scene_on_strips(scene, steps, world, halo_rows=halo)
+    assert len(multi) == len(ref)
+    assert_same_bits(multi, ref, f"scene {scene} on {world} strips")
+
+
+def test_state_injection_on_strips():
+    """sph_write_particles on strips (demo4.cpp:223-255 from an injected reference state): every rank is given the whole
+    state and keeps its window; then 12 steps equal the single-GPU run from the same injected state."""
+    import os
+
+    state = np.load(os.path.join(os.path.dirname(__file__), "golden", "scene0.npz"))["state8"]
+    ref = reference_scene_single(0, 12, inject=state)
+    multi = reference_scene_on_strips(0, 12, 2, inject=state)
+    assert_same_bits(multi, ref, "scene 0 from the reference's state after 8 steps, 2 strips")
