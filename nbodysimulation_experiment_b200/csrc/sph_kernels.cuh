@@ -866,11 +866,16 @@ __device__ __forceinline__ float2 butterfly_sum2_lane0(float x, float y, uint32_
 // third of the candidates are in range, so this removes most of the divergence of the expensive
 // part (sqrt, 1/r, the pair term).
 //
-// Shared memory per warp: sPos[cap] (+ sVel[cap] for viscosity) + queue[cap] (uint16).  A block with
+// Shared memory per warp: sPos[cap] (+ sVel[cap] for viscosity) + queue[cap] (uint16; two of them for viscosity, whose
+// range tests run for two particles at a time while that costs no occupancy, sweep_paired).  A block with
 // more than `cap` candidates is not staged: it reads and writes the sorted arrays through L2 and uses
 // the whole per-warp area as its queue, which bounds it at sweep_queue_capacity(cap) candidates
 // (the reference asserts at 1000, demo4.cpp:199).
-__host__ __device__ inline uint32_t sweep_bytes_per_warp(uint32_t cap, int pass) { return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) + cap * 2u; }
+#define SPH_PAIR_MAX_CAP 256u // up to this staging capacity the second queue is free: registers, not shared memory, limit the resident blocks
+__host__ __device__ inline bool sweep_paired(uint32_t cap, int pass) { return pass == SWEEP_VISCOSITY && cap <= SPH_PAIR_MAX_CAP; }
+__host__ __device__ inline uint32_t sweep_bytes_per_warp(uint32_t cap, int pass) {
+	return cap * 8u * (pass == SWEEP_VISCOSITY ? 2u : 1u) + cap * 2u * (sweep_paired(cap, pass) ? 2u : 1u);
+}
 __host__ __device__ inline uint32_t sweep_queue_capacity(uint32_t cap, int pass) { return sweep_bytes_per_warp(cap, pass) / 2u; }
 
 // One cell, one warp.  STAGED: the block's candidates live in shared memory (sPos/sVel, padded to a
@@ -890,7 +895,8 @@ struct SweepNoHook {
 };
 template <class M, int PASS, bool STAGED, bool COHERENT = false, class Hook = SweepNoHook>
 __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock &b, float2 *pos, float2 *vel, const float2 *__restrict__ press,
-                                           float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask, Hook beforeWriteBack = Hook()) {
+                                           float2 *sPos, float2 *sVel, uint16_t *queue, uint32_t lane, uint32_t ltMask, Hook beforeWriteBack = Hook(),
+                                           uint16_t *queueB = nullptr) {
 	float2 *state = (PASS == SWEEP_DELTA) ? pos : vel;
 	const uint32_t Tpad = (b.T + 31u) & ~31u;
 	if (STAGED) {
@@ -932,79 +938,104 @@ __device__ __forceinline__ void sweep_cell(const PairParams &k, const SweepBlock
 		}
 		__syncwarp();
 	}
+	// stage 2 of particle `ki` of the cell (slot si among the candidates): the pair terms of the queued candidates,
+	// partner updated at once (demo4.cpp:233-234, 250-251), then the particle's own change (demo4.cpp:253)
+	auto stage2 = [&](uint32_t ki, uint32_t si, float2 xi, float2 ppi, const uint16_t *q16, uint32_t nHit) {
+		float2 vi = make_float2(0.0f, 0.0f);
+		if (PASS == SWEEP_VISCOSITY) vi = STAGED ? sVel[si] : __ldcg(&vel[b.ownLo + ki]);
+		float2 acc = make_float2(0.0f, 0.0f);
+		for (uint32_t q = lane; q < nHit; q += 32) {
+			const uint32_t t = q16[q];
+			bool hit;
+			if (PASS == SWEEP_DELTA) {
+				float2 *slot = STAGED ? &sPos[t] : &pos[b.gidx(t)];
+				const float2 xj = STAGED ? *slot : __ldcg(slot);
+				const float2 hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit); // queued = within h, nothing moved it since stage 1
+				const float2 moved = Exact::add2(hlf, xj);
+				if (STAGED) *slot = moved;
+				else __stcg(slot, moved);
+				acc = Exact::sub2(acc, hlf);
+			} else {
+				const uint32_t j = STAGED ? 0u : b.gidx(t);
+				float2 *slot = STAGED ? &sVel[t] : &vel[j];
+				const float2 vj = STAGED ? *slot : __ldcg(slot);
+				const float2 xj = STAGED ? sPos[t] : __ldcg(&pos[j]);
+				const float2 hlf = sweep_viscosity_term<M, false>(k, xi, vi, xj, vj, hit);
+				if (hit) {
+					const float2 moved = Exact::add2(hlf, vj);
+					if (STAGED) *slot = moved;
+					else __stcg(slot, moved);
+					acc = Exact::sub2(acc, hlf);
+				}
+			}
+		}
+		const float2 own = butterfly_sum2_lane0(acc.x, acc.y, lane);
+		__syncwarp();
+		if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
+			if (STAGED) {
+				float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
+				*slot = make_float2(__fadd_rn(own.x, slot->x), __fadd_rn(own.y, slot->y));
+			} else {
+				float2 *slot = &state[b.ownLo + ki];
+				const float2 cur = __ldcg(slot);
+				__stcg(slot, make_float2(__fadd_rn(own.x, cur.x), __fadd_rn(own.y, cur.y)));
+			}
+		}
+		__syncwarp();
+	};
+	// The viscosity pass never moves a position, so the range tests (stage 1) of two consecutive particles of the cell
+	// can share one walk over the staged block - one load per 32 candidates for both - before their pair loops run one
+	// after the other; the displacement pass must test each particle against the positions the previous one left.
+	// (queueB: the second queue, where sweep_bytes_per_warp reserves one)
+	const bool paired = STAGED && PASS == SWEEP_VISCOSITY && queueB != nullptr;
 	for (uint32_t kBase = 0; kBase < b.m; kBase += 32) {
 		float2 myPress = make_float2(0.0f, 0.0f);
 		if (PASS == SWEEP_DELTA && kBase + lane < b.m) myPress = press[b.ownLo + kBase + lane];
 		const uint32_t kEnd = min(b.m - kBase, 32u);
-		for (uint32_t kk = 0; kk < kEnd; ++kk) {
+		for (uint32_t kk = 0; kk < kEnd; kk += (paired ? 2u : 1u)) {
 			const uint32_t si = b.ownOff + kBase + kk; // this particle's slot among the candidates
-			float2 xi, vi = make_float2(0.0f, 0.0f), ppi = make_float2(0.0f, 0.0f);
+			const bool two = paired && kk + 1u < kEnd;
+			float2 xi, xi2 = make_float2(3.0e18f, 3.0e18f), ppi = make_float2(0.0f, 0.0f);
 			if (STAGED) {
 				xi = sPos[si];
-				if (PASS == SWEEP_VISCOSITY) vi = sVel[si];
+				if (two) xi2 = sPos[si + 1u];
 			} else {
 				xi = __ldcg(&pos[b.ownLo + kBase + kk]);
-				if (PASS == SWEEP_VISCOSITY) vi = __ldcg(&vel[b.ownLo + kBase + kk]);
 			}
 			if (PASS == SWEEP_DELTA) {
 				ppi.x = __shfl_sync(0xffffffffu, myPress.x, (int)kk);
 				ppi.y = __shfl_sync(0xffffffffu, myPress.y, (int)kk);
 			}
 			// stage 1: which candidates are within h (sph.h:488,502)
-			uint32_t nHit = 0;
+			uint32_t nHit = 0, nHit2 = 0;
+			if (STAGED && PASS == SWEEP_VISCOSITY && two) {
 #pragma unroll 2
-			for (uint32_t tb = 0; tb < Tpad; tb += 32) {
-				const uint32_t t = tb + lane;
-				float2 xj;
-				if (STAGED) xj = sPos[t];
-				else xj = (t < b.T) ? __ldcg(&pos[b.gidx(t)]) : make_float2(3.0e18f, 3.0e18f);
-				const bool hit = M::norm2(M::sub2(xj, xi)) < k.h2;
-				const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-				if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
-				nHit += (uint32_t)__popc(mask);
-			}
-			__syncwarp();
-			// stage 2: the pair terms, partner updated at once (demo4.cpp:233-234, 250-251)
-			float2 acc = make_float2(0.0f, 0.0f);
-			for (uint32_t q = lane; q < nHit; q += 32) {
-				const uint32_t t = queue[q];
-				bool hit;
-				if (PASS == SWEEP_DELTA) {
-					float2 *slot = STAGED ? &sPos[t] : &pos[b.gidx(t)];
-					const float2 xj = STAGED ? *slot : __ldcg(slot);
-					const float2 hlf = sweep_delta_term<M, false>(k, xi, ppi, xj, hit); // queued = within h, nothing moved it since stage 1
-					const float2 moved = Exact::add2(hlf, xj);
-					if (STAGED) *slot = moved;
-					else __stcg(slot, moved);
-					acc = Exact::sub2(acc, hlf);
-				} else {
-					const uint32_t j = STAGED ? 0u : b.gidx(t);
-					float2 *slot = STAGED ? &sVel[t] : &vel[j];
-					const float2 vj = STAGED ? *slot : __ldcg(slot);
-					const float2 xj = STAGED ? sPos[t] : __ldcg(&pos[j]);
-					const float2 hlf = sweep_viscosity_term<M, false>(k, xi, vi, xj, vj, hit);
-					if (hit) {
-						const float2 moved = Exact::add2(hlf, vj);
-						if (STAGED) *slot = moved;
-						else __stcg(slot, moved);
-						acc = Exact::sub2(acc, hlf);
-					}
+				for (uint32_t tb = 0; tb < Tpad; tb += 32) {
+					const uint32_t t = tb + lane;
+					const float2 xj = sPos[t];
+					const bool hit = M::norm2(M::sub2(xj, xi)) < k.h2, hit2 = M::norm2(M::sub2(xj, xi2)) < k.h2;
+					const uint32_t mask = __ballot_sync(0xffffffffu, hit), mask2 = __ballot_sync(0xffffffffu, hit2);
+					if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
+					if (hit2) queueB[nHit2 + (uint32_t)__popc(mask2 & ltMask)] = (uint16_t)t;
+					nHit += (uint32_t)__popc(mask);
+					nHit2 += (uint32_t)__popc(mask2);
 				}
-			}
-			const float2 own = butterfly_sum2_lane0(acc.x, acc.y, lane);
-			float ax = own.x, ay = own.y;
-			__syncwarp();
-			if (lane == 0) { // curPosition += dx (demo4.cpp:253): dx + cur
-				if (STAGED) {
-					float2 *slot = (PASS == SWEEP_DELTA) ? &sPos[si] : &sVel[si];
-					*slot = make_float2(__fadd_rn(ax, slot->x), __fadd_rn(ay, slot->y));
-				} else {
-					float2 *slot = &state[b.ownLo + kBase + kk];
-					const float2 cur = __ldcg(slot);
-					__stcg(slot, make_float2(__fadd_rn(ax, cur.x), __fadd_rn(ay, cur.y)));
+			} else {
+#pragma unroll 2
+				for (uint32_t tb = 0; tb < Tpad; tb += 32) {
+					const uint32_t t = tb + lane;
+					float2 xj;
+					if (STAGED) xj = sPos[t];
+					else xj = (t < b.T) ? __ldcg(&pos[b.gidx(t)]) : make_float2(3.0e18f, 3.0e18f);
+					const bool hit = M::norm2(M::sub2(xj, xi)) < k.h2;
+					const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+					if (hit) queue[nHit + (uint32_t)__popc(mask & ltMask)] = (uint16_t)t;
+					nHit += (uint32_t)__popc(mask);
 				}
 			}
 			__syncwarp();
+			stage2(kBase + kk, si, xi, ppi, queue, nHit);
+			if (two) stage2(kBase + kk + 1u, si + 1u, xi2, ppi, queueB, nHit2);
 		}
 	}
 	beforeWriteBack();
@@ -1062,7 +1093,7 @@ __global__ void __launch_bounds__(SPH_SWEEP_WARPS * 32) color_sweep_kernel(GridD
 		const uint32_t c = colour_cell(colorList, listStride, nLight, idx);
 		const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
 		if (((b.T + 31u) & ~31u) <= cap) {
-			sweep_cell<M, PASS, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask);
+			sweep_cell<M, PASS, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask, SweepNoHook(), sweep_paired(cap, PASS) ? queueStaged + cap : nullptr);
 		} else if (b.T <= wideCap) {
 			sweep_cell<M, PASS, false>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask);
 			__syncwarp();
@@ -1365,7 +1396,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		uint32_t nextTicket = 0;
 		auto draw_next = [&]() { nextTicket = draw_ticket(); };
 		if (((b.T + 31u) & ~31u) <= cap) {
-			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask, draw_next);
+			sweep_cell<M, PASS, true, true>(k, b, pos, vel, press, sPos, sVel, queueStaged, lane, ltMask, draw_next, sweep_paired(cap, PASS) ? queueStaged + cap : nullptr);
 		} else if (b.T <= wideCap) { // (only when the lists were classified for a larger staging capacity than this launch has)
 			sweep_cell<M, PASS, false, true>(k, b, pos, vel, press, sPos, sVel, queueWide, lane, ltMask, draw_next);
 		} else { // denser than anything the queue can hold: report, leave the cell alone
