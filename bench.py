@@ -55,7 +55,7 @@ PHASE_BYTES = {"integrate": 16, "viscosity": 24, "predict_key": 36, "scan": 0, "
 # integrate, viscosity sweep (1 launch, or 9 with --sweep warp/team), predict_key, scan (tile sums, apply), colour lists (count, fill),
 # scatter_ids, reorder, density, delta sweep (1 or 9), collide_velocity
 KERNELS_PER_STEP = {"gs": 12, "gs9": 28, "gather": 10}
-TRAFFIC_FILE = "r1_final_traffic.json"  # ncu --set full figures of the dominant kernel on the default workload
+TRAFFIC_FILE = "r2_traffic.json"  # ncu --set full figures of the dominant kernel on the default workload (tools/summarize_ncu.py traffic)
 
 
 def scene_gravity(nx, spacing, scaled):

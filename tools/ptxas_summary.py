@@ -16,7 +16,7 @@ from nbodysimulation_experiment_b200 import build  # noqa: E402
 
 def demangle(names):
     out = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
-    return [re.sub(r"\(.*", "", o).replace("void ", "").replace("sphb200::", "").replace("(anonymous namespace)::", "") for o in out]
+    return [re.sub(r"\(.*", "", o.replace("(anonymous namespace)::", "")).replace("void ", "").replace("sphb200::", "") for o in out]
 
 
 def main():
