@@ -47,7 +47,7 @@ def load_state():
     return p, old_rows
 
 
-def worker(rank, port, out_dir):
+def worker(rank, port, out_dir, WORLD=WORLD):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     p, old_rows = load_state()
@@ -83,6 +83,16 @@ def worker(rank, port, out_dir):
             r.wait()
         recv.append(got.numpy())
     got = np.concatenate(recv) if recv else np.zeros((0, 13))
+    # where the device files what arrived (unpack_kernel): behind the kept particles, the lower neighbour's records first,
+    # the upper neighbour's behind THEM - an interior strip (two neighbours) is the case two ranks never exercise
+    n_keep = int(keep.sum())
+    offsets = np.cumsum([n_keep] + [len(r) for r in recv])
+    assert offsets[-1] == n_keep + len(got) and len(recv) == (rank > 0) + (rank + 1 < WORLD)
+    if 0 < rank < WORLD - 1:
+        assert len(recv) == 2 and len(recv[0]) > 0 and len(recv[1]) > 0, "an interior strip must hear from both neighbours"
+        lower_rows = strips.cell_rows(recv[0][:, 2].astype(np.float32), HALF_H, CELL, GRID_Y)
+        upper_rows = strips.cell_rows(recv[1][:, 2].astype(np.float32), HALF_H, CELL, GRID_Y)
+        assert lower_rows.max() < upper_rows.min(), "records of the two neighbours come from opposite ends of the window"
     local_ids = np.concatenate([my_ids[keep], got[:, 0].astype(np.int64)])
     local_rec = np.concatenate([my_rec[keep], got[:, 1:].astype(np.float32)])
     assert len(np.unique(local_ids)) == len(local_ids), "a particle arrived twice"
@@ -104,11 +114,13 @@ def worker(rank, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_exchange_protocol(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_protocol_over_gloo(tmp_path, world):
+    """two ranks: every strip has one neighbour; three ranks: the middle strip has two"""
     port = free_port()
-    mp.spawn(worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    mp.spawn(worker, args=(port, str(tmp_path), world), nprocs=world, join=True)
     p, _ = load_state()
-    parts = [(np.load(tmp_path / f"ids{r}.npy"), np.load(tmp_path / f"rec{r}.npy")) for r in range(WORLD)]
+    parts = [(np.load(tmp_path / f"ids{r}.npy"), np.load(tmp_path / f"rec{r}.npy")) for r in range(world)]
     assert all(len(a) > 0 for a, _ in parts)
     merged = strips.merge_owned(parts, len(p))
     assert np.array_equal(merged, p)
