@@ -455,7 +455,12 @@ def run_reference(args):
 
     build_oracle()
     wl = WORKLOADS[args.workload]
-    nx = args.nx or wl["nx"]
+    nx_one = args.nx or wl["nx"]
+    # the same scene as our arm at this GPU count (weak scaling: the block grows with N, see run_ours)
+    world = max(args.gpus, 1)
+    nx = nx_one if world == 1 else int(round(nx_one * world ** 0.5 / 32.0)) * 32
+    if args.nx_total:
+        nx = args.nx_total
     spacing = wl["spacing"]
     gravity = scene_gravity(nx, spacing, wl["gravity_scale"] or args.scaled_gravity)
     cores = os.cpu_count() or 1

@@ -145,6 +145,7 @@ __device__ __forceinline__ uint32_t for_each_candidate(const GridDesc &g, const 
 		const uint32_t base = (uint32_t)(y - g.rowLo) * (uint32_t)g.gx;
 		const uint32_t lo = cellStart[base + x0], hi = cellStart[base + x1 + 1];
 		total += hi - lo;
+#pragma unroll 4
 		for (uint32_t j = lo; j < hi; ++j) body(j);
 	}
 	return total;

@@ -153,6 +153,7 @@ struct SphSim {
 	uint32_t teamDiv = 2;            // at most 1/teamDiv of the sweep's blocks work as teams
 	float capFactor = 2.2f;          // per-warp staging capacity as a multiple of the average candidate list
 	float capAvg = 0.0f;             // candidates per particle the adaptive capacity was last chosen for
+	bool capMeasured = false;        // ... from a measurement (not from the scene's nominal density)
 	bool sweepAdaptive = true;       // pick the staging capacity from the candidates per particle of recent steps
 	Counters *hCtrLag = nullptr;     // pinned, refreshed asynchronously after every step
 	cudaEvent_t lagEvent = nullptr;
@@ -1537,6 +1538,9 @@ struct StepCtx {
 // staging capacity and heavy-cell threshold for `avg` candidates per particle (step_prepare)
 void set_sweep_class(SphSim *s, float avg) {
 	s->capAvg = avg;
+	// decisions are taken on the average rounded to a 10 % geometric grid: a measured 80.7 after a nominal 81 must not
+	// produce a new threshold, hence a new step graph
+	avg = expf(roundf(logf(std::max(avg, 1.0f)) / logf(1.1f)) * logf(1.1f));
 	if (s->sweepAdaptive) {
 		static const uint32_t steps[] = { 256, 384, 512, 768, 1024 };
 		uint32_t cap = 1024;
@@ -1581,7 +1585,12 @@ int step_prepare(SphSim *s, float dt, StepCtx &c, bool planRebalance, bool emit 
 		// every new capacity is a new step graph.  A cell is also heavy from 6 x the average work m x T (m ~ T / 9).
 		const Counters &lag = *s->hCtrLag;
 		const float avg = lag.nOut ? (float)((double)lag.pairCandidates / (double)lag.nOut) : 0.0f;
-		if (avg > 0.0f && (s->capAvg == 0.0f || avg > 1.3f * s->capAvg || avg < 0.7f * s->capAvg)) set_sweep_class(s, avg);
+		// the first measurement replaces the nominal density whatever it says (a jittered lattice has ~25 % fewer
+		// candidates than 9 full cells), later ones only outside a +-30 % band
+		if (avg > 0.0f && (s->capAvg == 0.0f || !s->capMeasured || avg > 1.3f * s->capAvg || avg < 0.7f * s->capAvg)) {
+			set_sweep_class(s, avg);
+			s->capMeasured = true;
+		}
 		s->lagPending = false;
 	}
 	c.dt = dt;
