@@ -77,6 +77,7 @@ class ClockSampler:
         self.device = device
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self.stop_flag = threading.Event()
+        self.armed = False  # samples count only while armed (the thread is started ahead of the timed region)
         self.thread = None
         self.nvml = None
         try:
@@ -98,11 +99,13 @@ class ClockSampler:
         nv = self.nvml
         while not self.stop_flag.is_set():
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                clock = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                for name, bit in self.REASONS:
-                    if mask & bit:
-                        self.reasons.add(name)
+                if self.armed:
+                    self.sm.append(clock)
+                    for name, bit in self.REASONS:
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             self.stop_flag.wait(0.02)
@@ -206,24 +209,50 @@ def run_ours(args):
         for _ in range(warmup):
             sim.Update(DT)
         flush.fill_(1)
-        barrier()
-        # clocks are sampled on rank 0 only (its numbers are the ones reported): eight processes polling NVML inside
-        # a 15 ms timed region contend for the driver and cost every rank ~6 % (profiles/bench_r2)
+        # Everything slow goes BEFORE the barrier: on strips a rank that enters the timed loop late keeps its neighbours
+        # waiting inside their first step (they need its halo records), and the wait then travels up the strips one rank
+        # per step.  (Measured, profiles/bench_r2/r2w_*: NVML initialisation between the barrier and the first step
+        # on every rank cost 2-3.5 ms in the first step of half the ranks, 0.70 -> 0.84 ms/step over 20 steps.)
+        # Clocks are sampled on rank 0 only (its numbers are the ones reported): eight processes polling NVML inside
+        # a 15 ms timed region contend for the driver and cost every rank ~6 %.
         sample_clocks = not args.no_clock_sampler and rank == 0
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
         if sample_clocks:
-            sampler.start()
+            sampler.start()  # polls from now on, keeps samples only while armed
+        per_step = None
+        if args.per_step:  # diagnostic: an event between the steps (recorded on the simulation's stream, read after the region)
+            stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local_rank))
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        host_ms = []
+        barrier()
+        if sample_clocks:
+            sampler.armed = True
         sim.mark(0)
-        for _ in range(steps):
+        for k in range(steps):
+            if args.per_step:
+                evs[k].record(stream)
+                h0 = time.perf_counter()
             sim.Update(DT)
+            if args.per_step:
+                host_ms.append(round((time.perf_counter() - h0) * 1e3, 3))
+        if args.per_step:
+            evs[steps].record(stream)
         sim.mark(1)
         ms = sim.elapsed_ms(0, 1)
+        if args.per_step:
+            mine = {"rank": rank, "device_ms": [round(evs[k].elapsed_time(evs[k + 1]), 3) for k in range(steps)], "host_ms": host_ms}
+            per_step = [mine]
+            if world > 1:
+                per_step = [None] * world
+                dist.all_gather_object(per_step, mine)
+        if sample_clocks:
+            sampler.armed = False
         barrier()
         clocks = sampler.stop() if sample_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler disabled" if rank == 0 else "sampled on rank 0"]}
         ms = all_max(ms)
         stats = sim.GetStats()  # raises if a capacity / lost / timeout flag was set on the device
         out = {"nx": nx, "n_total": n_total, "n_local": n_local, "cells": gx * gy, "grid": (gx, gy), "gravity": gravity, "ms": ms, "steps": steps,
-               "value": n_total * steps / (ms * 1e-3), "clocks": clocks, "candidates": stats.pair_candidates / max(n_local, 1)}
+               "value": n_total * steps / (ms * 1e-3), "clocks": clocks, "candidates": stats.pair_candidates / max(n_local, 1), "per_step_ms": per_step}
 
         # ---- e2e: Update + Render readback (positions + colours) into host memory every step, the per-frame
         # traffic of the reference's app loop (app.cpp:231-233,286-289).  One GPU: creation-order arrays in pinned
@@ -383,6 +412,8 @@ def run_ours(args):
             "phases_ms": phases,
             "cpu_baseline": cpu,
         }
+        if main.get("per_step_ms"):
+            line["per_step"] = main["per_step_ms"]
         if c4:
             line.update({"c4_value": c4["value"], "c4_ms_per_step": c4["ms"] / c4["steps"], "c4_e2e": c4["e2e"], "c4_particles_rank0": c4["n_local"],
                          "c4_clocks": c4["clocks"]})
@@ -516,6 +547,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="strip exchange: records stored straight into the neighbour's memory (default) or fixed-size NCCL messages")
     ap.add_argument("--scaled-gravity", action="store_true", help="scale gravity to the reference scene's hydrostatic head")
+    ap.add_argument("--per-step", action="store_true", help="diagnostic: also report every rank's device and host time of every timed step (per_step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
