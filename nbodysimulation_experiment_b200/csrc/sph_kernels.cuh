@@ -1336,7 +1336,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		uint32_t mostHeavy = 0;
 #pragma unroll
 		for (int cc = 0; cc < 9; ++cc) mostHeavy = max(mostHeavy, counts[9 + cc]);
-		const uint32_t teams = mostHeavy ? max(1u, min(mostHeavy, min(maxTeams, gridDim.x / 2u))) : 0u;
+		const uint32_t teams = mostHeavy ? max(1u, min(mostHeavy, min(maxTeams, gridDim.x - 1u))) : 0u; // (the host keeps a share of the blocks for the light queue)
 		if (blockIdx.x < teams) {
 			const uint32_t capTeam = team_capacity(SPH_FLOW_WARPS * sweep_bytes_per_warp(cap, PASS), PASS);
 			uint32_t *teamTickets = flow + 2u + (epoch & 1u);

@@ -150,7 +150,7 @@ struct SphSim {
 	uint32_t gridSweepCap = 256;     // the staging capacity the current grid's lists were classified for (light cells fit it)
 	uint32_t workHeavy = 6000;       // m x T from which a cell is swept by a whole block (SweepClass)
 	float heavyFactor = 6.0f;        // ... as a multiple of the average m x T
-	uint32_t teamDiv = 2;            // at most 1/teamDiv of the sweep's blocks work as teams
+	float teamFrac = 0.5f;           // at most this share of the sweep's blocks work as teams (never more than 7/8: the light queue needs workers)
 	float capFactor = 2.2f;          // per-warp staging capacity as a multiple of the average candidate list
 	float capAvg = 0.0f;             // candidates per particle the adaptive capacity was last chosen for
 	bool capMeasured = false;        // ... from a measurement (not from the scene's nominal density)
@@ -626,7 +626,7 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 		const unsigned blocks = (unsigned)std::max<uint64_t>(2, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
 		color_sweep_flow_kernel<M, PASS><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
 		                                                                                 s->vel.in(), s->press.in(), cap, s->dCtr, s->sweepFlow, ++s->flowEpoch,
-		                                                                                 std::max(1u, blocks / s->teamDiv));
+		                                                                                 std::max(1u, std::min(blocks - std::max(1u, blocks / 8u), (unsigned)((float)blocks * s->teamFrac))));
 		return;
 	}
 	for (int color = 0; color < 9; ++color) {
@@ -958,7 +958,7 @@ int sph_create(const SphConfig *cfg, SphHandle *out) {
 	s->sweepAdaptive = cfg->sweep_capacity == 0;
 	s->useGraphs = !(cfg->flags & SPH_FLAG_NO_GRAPHS);
 	if (const char *e = getenv("SPHB200_HEAVY_FACTOR")) s->heavyFactor = std::max(1.0f, (float)atof(e)); // tuning knobs of the light / heavy split
-	if (const char *e = getenv("SPHB200_TEAM_DIV")) s->teamDiv = (uint32_t)std::max(2, atoi(e));
+	if (const char *e = getenv("SPHB200_TEAM_FRAC")) s->teamFrac = std::min(0.875f, std::max(0.01f, (float)atof(e)));
 	if (const char *e = getenv("SPHB200_CAP_FACTOR")) s->capFactor = std::max(1.0f, (float)atof(e));
 	{
 		// the viscosity sweep stages positions + velocities + a 16-bit queue: 18 bytes per candidate and warp
