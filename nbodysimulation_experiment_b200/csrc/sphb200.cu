@@ -2212,7 +2212,7 @@ int sph_read_owned(SphHandle s, uint32_t *ids, void *records, size_t recStride, 
 }
 // The strip counterpart of sph_render_particles: snapshot of the owned particles (ids, positions, colours) on the
 // simulation's stream, device-to-host copies on the copy stream, so the next sph_step overlaps them.  The number of
-// owned particles only exists on the device; the copies ship 1.1 x the previous frame's count (+4096) and
+// owned particles only exists on the device; the copies ship 1.02 x the previous frame's count (+4096) and
 // sph_wait_render_owned fetches the rest in the rare frame that outgrew it.  The first frame is read synchronously.
 int sph_render_owned(SphHandle s, uint32_t *ids, void *positions, size_t posStride, void *colors, size_t colStride) {
 	ENTER(s);
@@ -2250,7 +2250,7 @@ int sph_render_owned(SphHandle s, uint32_t *ids, void *positions, size_t posStri
 	CU(s, cudaGetLastError());
 	CU(s, cudaEventRecord(s->renderReady, s->stream));
 	CU(s, cudaStreamWaitEvent(s->copyStream, s->renderReady, 0));
-	const uint64_t ship = std::min<uint64_t>(cap, s->ownedLast + s->ownedLast / 10 + 4096);
+	const uint64_t ship = std::min<uint64_t>(cap, s->ownedLast + s->ownedLast / 50 + 4096); // a strip's population changes by far less than 2 % per frame
 	CU(s, cudaMemcpyAsync(s->hOwnedCount, s->dOwnedCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
 	CU(s, cudaMemcpyAsync(ids, s->dOwnedIds, (size_t)ship * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
 	CU(s, copy_strided(positions, posStride, s->dRenderPos, sizeof(float2), sizeof(float2), (size_t)ship, cudaMemcpyDeviceToHost, s->copyStream));
@@ -2267,7 +2267,7 @@ int sph_wait_render_owned(SphHandle s, uint64_t *count) {
 	if (!s->ownedPending) return fail(s, SPH_ERR_STATE, "no sph_render_owned frame in flight");
 	if (s->copyPending) CU(s, cudaEventSynchronize(s->copyDone));
 	const uint64_t n = std::min<uint64_t>(*s->hOwnedCount, s->capacity);
-	if (n > s->ownedShipped) { // the strip grew by more than 10 % in one frame: fetch the tail (the snapshot is still intact)
+	if (n > s->ownedShipped) { // the strip grew by more than 2 % in one frame: fetch the tail (the snapshot is still intact)
 		const size_t from = (size_t)s->ownedShipped, more = (size_t)(n - s->ownedShipped);
 		CU(s, cudaMemcpyAsync(s->ownedIdsDst + from, s->dOwnedIds + from, more * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copyStream));
 		CU(s, copy_strided((char *)s->ownedPosDst + from * s->ownedPosStride, s->ownedPosStride, s->dRenderPos + from, sizeof(float2), sizeof(float2), more,
