@@ -872,29 +872,33 @@ int append_particles_owned(SphSim *s, size_t n, const float *posXY, const float 
 	if (firstIndex) *firstIndex = s->nextId;
 	if (n == 0) return SPH_OK;
 	if (s->nextId + n > 0xFFFFFF00ull) return fail(s, SPH_ERR_CAPACITY, "particle ids exceed 32 bits");
-	float2 *dPos = nullptr, *dAcc = nullptr;
-	ParticleRecord *dRec = nullptr;
+	struct Staging { // device copies of the host lists, released on every way out
+		float2 *pos = nullptr, *acc = nullptr;
+		ParticleRecord *rec = nullptr;
+		~Staging() {
+			cudaFree(pos);
+			cudaFree(acc);
+			cudaFree(rec);
+		}
+	} d;
 	if (records) {
-		CU(s, cudaMalloc(&dRec, n * sizeof(ParticleRecord)));
-		CU(s, copy_strided(dRec, sizeof(ParticleRecord), records, recStride, sizeof(ParticleRecord), n, cudaMemcpyHostToDevice, s->stream));
+		CU(s, cudaMalloc(&d.rec, n * sizeof(ParticleRecord)));
+		CU(s, copy_strided(d.rec, sizeof(ParticleRecord), records, recStride, sizeof(ParticleRecord), n, cudaMemcpyHostToDevice, s->stream));
 	} else {
-		CU(s, cudaMalloc(&dPos, n * sizeof(float2)));
-		CU(s, cudaMemcpyAsync(dPos, posXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+		CU(s, cudaMalloc(&d.pos, n * sizeof(float2)));
+		CU(s, cudaMemcpyAsync(d.pos, posXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
 		if (accXY) {
-			CU(s, cudaMalloc(&dAcc, n * sizeof(float2)));
-			CU(s, cudaMemcpyAsync(dAcc, accXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+			CU(s, cudaMalloc(&d.acc, n * sizeof(float2)));
+			CU(s, cudaMemcpyAsync(d.acc, accXY, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
 		}
 	}
 	const bool window = records != nullptr; // an injected state also fills the ghost rows (see append_owned_kernel)
 	append_owned_kernel<<<blocks_for(n), SPH_THREADS, 0, s->stream>>>(s->grid, window ? s->grid.rowLo : s->grid.ownLo, window ? s->grid.rowHi : s->grid.ownHi, s->dCtr,
-	                                                                s->capacity, (uint32_t)n, dPos, dAcc, dRec, (uint32_t)s->nextId, s->pos.in(),
+	                                                                s->capacity, (uint32_t)n, d.pos, d.acc, d.rec, (uint32_t)s->nextId, s->pos.in(),
 	                                                                s->prev.in(), s->vel.in(), s->acc.in(), s->dens.in(), s->press.in(), s->id.in());
 	clamp_count_kernel<<<1, 1, 0, s->stream>>>(s->dCtr, s->capacity);
 	CU(s, cudaGetLastError());
 	CU(s, cudaStreamSynchronize(s->stream)); // the pageable sources and the staging buffers must outlive the copies
-	cudaFree(dPos);
-	cudaFree(dAcc);
-	cudaFree(dRec);
 	s->accFrom = 0u;
 	s->nextId += n;
 	return SPH_OK;
