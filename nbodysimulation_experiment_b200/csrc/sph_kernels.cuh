@@ -1331,6 +1331,12 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 		return __ldg(&colorList[(size_t)base + (cls ? listStride - 1u - at : at)]);
 	};
 
+	// Strips: the viscosity sweep is the LAST sweep before the next exchange drops every ghost, so only the owned rows
+	// have to come out right, and an error travels at most three rows inward per sweep (the halo bound of DESIGN.md
+	// section 7): ghost cells more than three rows away from the owned rows are marked done without being swept.
+	const uint32_t sweptLo = PASS == SWEEP_VISCOSITY ? (uint32_t)(max(g.ownLo - 3, g.rowLo) - g.rowLo) * (uint32_t)g.gx : 0u;
+	const uint32_t sweptHi = PASS == SWEEP_VISCOSITY ? (uint32_t)(min(g.ownHi + 3, g.rowHi) - g.rowLo) * (uint32_t)g.gx : 0xffffffffu;
+
 	// ---- heavy cells: the first `teams` blocks, one block per cell --------------------------------------------
 	{
 		uint32_t mostHeavy = 0;
@@ -1345,6 +1351,11 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 				__syncthreads();
 				const uint32_t c = cell_of_ticket(teamTicket, 1u);
 				if (c == SPH_KEY_NONE) break; // (uniform: every thread read the same ticket)
+				if (c < sweptLo || c >= sweptHi) { // a far ghost cell: nothing to sweep, nobody needs to wait for it
+					__syncthreads(); // (everybody has read the ticket)
+					if (threadIdx.x == 0) st_release_gpu(flags + c, epoch);
+					continue;
+				}
 				const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
 				if (w == 0) {
 					const uint32_t *flag = flow_pending_flag(g, flags, c, nRows, epoch, lane);
@@ -1386,6 +1397,11 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	};
 	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0), 0u);
 	while (c != SPH_KEY_NONE) {
+		if (c < sweptLo || c >= sweptHi) { // a far ghost cell (see above)
+			if (lane == 0) st_release_gpu(flags + c, epoch);
+			c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0), 0u);
+			continue;
+		}
 		const SweepBlock b = sweep_block_of(g, cellStart, c, nRows);
 		// (the flags are fetched together with the loads above: one round trip to L2 for all of them)
 		const uint32_t *flag = flow_pending_flag(g, flags, c, nRows, epoch, lane);
