@@ -95,19 +95,27 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def sample_now(self):
+        """one sample from the calling thread: bench.py takes it right after the last timed step is enqueued, when the
+        host has nothing to do and the GPU is busy with the queued steps - a timed region shorter than the polling period
+        still gets a sample under load"""
+        if not self.nvml:
+            return
         nv = self.nvml
+        try:
+            clock = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            self.sm.append(clock)
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop_flag.is_set():
-            try:
-                clock = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                if self.armed:
-                    self.sm.append(clock)
-                    for name, bit in self.REASONS:
-                        if mask & bit:
-                            self.reasons.add(name)
-            except Exception:
-                pass
+            if self.armed:
+                self.sample_now()
             self.stop_flag.wait(0.02)
 
     def start(self):
@@ -120,7 +128,7 @@ class ClockSampler:
             self.stop_flag.set()
             self.thread.join(timeout=1.0)
             return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "how": "NVML polled every 20 ms inside the timed region"}
+                    "samples": len(self.sm), "how": "NVML polled every 20 ms inside the timed region, plus once after the last step was enqueued"}
         try:  # one-shot fallback right after the region
             out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active", "--format=csv,noheader,nounits",
                                   "-i", str(self.device)], capture_output=True, text=True, timeout=10).stdout.strip().split(",")
@@ -238,6 +246,8 @@ def run_ours(args):
         if args.per_step:
             evs[steps].record(stream)
         sim.mark(1)
+        if sample_clocks:
+            sampler.sample_now()  # the device is still working through the queued steps
         ms = sim.elapsed_ms(0, 1)
         if args.per_step:
             mine = {"rank": rank, "device_ms": [round(evs[k].elapsed_time(evs[k + 1]), 3) for k in range(steps)], "host_ms": host_ms}

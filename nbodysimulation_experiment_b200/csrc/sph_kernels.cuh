@@ -1294,7 +1294,8 @@ __device__ __forceinline__ const uint32_t *flow_pending_flag(const GridDesc &g, 
 	return nullptr;
 }
 
-template <class M, int PASS>
+// STRIP: the launch runs on a y-strip (ghost rows exist); a single-GPU launch does not pay for the test below.
+template <class M, int PASS, bool STRIP>
 __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
     color_sweep_flow_kernel(GridDesc g, PairParams k, const uint32_t *__restrict__ cellStart, const uint32_t *__restrict__ colorList, uint32_t listStride,
                             const uint32_t *__restrict__ colorCount, float2 *pos, float2 *vel, const float2 *__restrict__ press, uint32_t cap,
@@ -1334,8 +1335,8 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	// Strips: the viscosity sweep is the LAST sweep before the next exchange drops every ghost, so only the owned rows
 	// have to come out right, and an error travels at most three rows inward per sweep (the halo bound of DESIGN.md
 	// section 7): ghost cells more than three rows away from the owned rows are marked done without being swept.
-	const uint32_t sweptLo = PASS == SWEEP_VISCOSITY ? (uint32_t)(max(g.ownLo - 3, g.rowLo) - g.rowLo) * (uint32_t)g.gx : 0u;
-	const uint32_t sweptHi = PASS == SWEEP_VISCOSITY ? (uint32_t)(min(g.ownHi + 3, g.rowHi) - g.rowLo) * (uint32_t)g.gx : 0xffffffffu;
+	const uint32_t sweptLo = (STRIP && PASS == SWEEP_VISCOSITY) ? (uint32_t)(max(g.ownLo - 3, g.rowLo) - g.rowLo) * (uint32_t)g.gx : 0u;
+	const uint32_t sweptHi = (STRIP && PASS == SWEEP_VISCOSITY) ? (uint32_t)(min(g.ownHi + 3, g.rowHi) - g.rowLo) * (uint32_t)g.gx : 0xffffffffu;
 
 	// ---- heavy cells: the first `teams` blocks, one block per cell --------------------------------------------
 	{
@@ -1351,7 +1352,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 				__syncthreads();
 				const uint32_t c = cell_of_ticket(teamTicket, 1u);
 				if (c == SPH_KEY_NONE) break; // (uniform: every thread read the same ticket)
-				if (c < sweptLo || c >= sweptHi) { // a far ghost cell: nothing to sweep, nobody needs to wait for it
+				if (STRIP && PASS == SWEEP_VISCOSITY && (c < sweptLo || c >= sweptHi)) { // a far ghost cell: nothing to sweep, nobody needs to wait for it
 					__syncthreads(); // (everybody has read the ticket)
 					if (threadIdx.x == 0) st_release_gpu(flags + c, epoch);
 					continue;
@@ -1397,7 +1398,7 @@ __global__ void __launch_bounds__(SPH_FLOW_WARPS * 32, SPH_FLOW_MIN_BLOCKS)
 	};
 	uint32_t c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0), 0u);
 	while (c != SPH_KEY_NONE) {
-		if (c < sweptLo || c >= sweptHi) { // a far ghost cell (see above)
+		if (STRIP && PASS == SWEEP_VISCOSITY && (c < sweptLo || c >= sweptHi)) { // a far ghost cell (see above)
 			if (lane == 0) st_release_gpu(flags + c, epoch);
 			c = cell_of_ticket(__shfl_sync(0xffffffffu, draw_ticket(), 0), 0u);
 			continue;

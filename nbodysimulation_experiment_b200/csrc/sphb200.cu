@@ -596,13 +596,14 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 		const int smem = (int)s->maxDynSmem;
 		cudaFuncSetAttribute(color_sweep_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(color_sweep_team_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(color_sweep_flow_kernel<M, PASS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		// resident blocks per SM of the persistent kernel for every staging capacity (32..3072 in steps of 32), asked
 		// once here: the first steps of a simulation are never inside a graph capture
 		for (uint32_t c32 = 1; c32 <= 96; ++c32) {
 			int nbk = 0;
 			const size_t bytes = (size_t)SPH_FLOW_WARPS * sweep_bytes_per_warp(c32 * 32u, PASS);
-			if (bytes <= s->maxDynSmem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, color_sweep_flow_kernel<M, PASS>, SPH_FLOW_WARPS * 32, bytes);
+			if (bytes <= s->maxDynSmem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, color_sweep_flow_kernel<M, PASS, true>, SPH_FLOW_WARPS * 32, bytes);
 			flowBlocksPerSM[c32] = nbk;
 		}
 		cudaGetLastError();
@@ -624,9 +625,14 @@ void launch_sweeps(SphSim *s, const PairParams &k) {
 		const uint64_t want = (9 * cells + SPH_FLOW_WARPS - 1) / SPH_FLOW_WARPS;
 		// at least two blocks: heavy cells are swept by the first blocks of the grid as teams, the others must be there for the light ones
 		const unsigned blocks = (unsigned)std::max<uint64_t>(2, std::min<uint64_t>(want, (uint64_t)occBlocks * (uint64_t)numSMs));
-		color_sweep_flow_kernel<M, PASS><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
-		                                                                                 s->vel.in(), s->press.in(), cap, s->dCtr, s->sweepFlow, ++s->flowEpoch,
-		                                                                                 std::max(1u, std::min(blocks - std::max(1u, blocks / 8u), (unsigned)((float)blocks * s->teamFrac))));
+		const unsigned maxTeams = std::max(1u, std::min(blocks - std::max(1u, blocks / 8u), (unsigned)((float)blocks * s->teamFrac)));
+		const uint32_t epoch = ++s->flowEpoch;
+		if (s->cfg.world_size > 1) // (the strip variant leaves far ghost cells out of the viscosity sweep)
+			color_sweep_flow_kernel<M, PASS, true><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
+			                                                                                       s->vel.in(), s->press.in(), cap, s->dCtr, s->sweepFlow, epoch, maxTeams);
+		else
+			color_sweep_flow_kernel<M, PASS, false><<<blocks, SPH_FLOW_WARPS * 32, smem, s->stream>>>(s->grid, k, s->cellStart, s->colorList, s->listStride, s->colorCount, s->pos.in(),
+			                                                                                        s->vel.in(), s->press.in(), cap, s->dCtr, s->sweepFlow, epoch, maxTeams);
 		return;
 	}
 	for (int color = 0; color < 9; ++color) {

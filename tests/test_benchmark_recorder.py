@@ -29,9 +29,11 @@ def check(doc, impl, particles):
     u = doc["update_ms"]
     assert 0.0 < u["min"] <= u["avg"] <= u["max"]
     assert doc["particle_steps_per_s_avg"] > 0
-    # the pair passes are where the time goes, whatever runs them
-    heavy = sum(doc["phases_ms"][k]["avg"] for k in ("viscosityForces", "neighborSearch", "densityAndPressure", "deltaPositions"))
-    assert heavy > 0.5 * sum(b["avg"] for b in doc["phases_ms"].values())
+    # on the CPU the pair passes are where the time goes (27 of 28 ms in the survey's probe); on the GPU a 1400-particle
+    # scene is launch-latency bound in every phase, so no share is asserted there (a timing assertion would be flaky)
+    if impl != "b200":
+        heavy = sum(doc["phases_ms"][k]["avg"] for k in ("viscosityForces", "neighborSearch", "densityAndPressure", "deltaPositions"))
+        assert heavy > 0.5 * sum(b["avg"] for b in doc["phases_ms"].values())
 
 
 def test_recorder_on_the_oracle_in_reference_semantics():
